@@ -1,0 +1,234 @@
+/*
+ * nextsearch_b200.h — C ABI of the B200-native BM25 scoring + top-k path.
+ *
+ * This is the drop-in boundary for NextSearch's query-time hot path
+ * (reference: src/api_engine.cpp:426-505, "for segId … score[docId] += … / top-K heap").
+ * The reference has no FFI; the seam it offers is the pair of Engine members
+ *   bool  Engine::reload()                      (include/api_engine.hpp:65, src/api_engine.cpp:50-162)
+ *   json  Engine::search(const string&, int k)  (include/api_engine.hpp:66, src/api_engine.cpp:369-542)
+ * and, one level down, the inner loop over (segment, query term, posting).
+ * The entry points below are what a cgo/JNI/ctypes/C++ binding for that seam
+ * would bind.  Plain pointers and sizes only; no C++ / torch types; no
+ * exceptions cross this boundary; every call returns an ns_status.
+ *
+ * Two layers:
+ *   ns_index_* / ns_batch_* / ns_search_batch / ns_merge_*   — the device path
+ *       proper: segments become device-resident CSR arrays, a batch of
+ *       lexicon-resolved queries is scored and top-k selected on the GPU.
+ *   ns_engine_*  — host mirror of cord19::Engine (reads the real on-disk
+ *       format, tokenises, resolves the lexicon, computes IDF with the host's
+ *       logf, calls the device path, packages the reference's JSON fields).
+ *   ns_corpus_* / ns_text_*  — the synthetic-corpus generator / segment writer
+ *       (replaces include/segment_writer.hpp:23-169 for large corpora) and the
+ *       tokenizer (include/textutil.hpp:13-37), exposed for tests and bench.
+ *
+ * Tie-break (total order, stated in DESIGN.md): score desc, then global
+ * segment index asc, then docId asc.  Scores are the exact f32 values the
+ * reference computes (same operation tree, round-to-nearest, no FMA).
+ */
+#ifndef NEXTSEARCH_B200_H
+#define NEXTSEARCH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum ns_status {
+    NS_OK = 0,
+    NS_ERR_INVALID = 1,      /* bad argument (null pointer, k out of range after clamp, too many terms …) */
+    NS_ERR_CUDA = 2,         /* CUDA runtime error or no usable device; ns_last_error() has the text */
+    NS_ERR_IO = 3,           /* missing / truncated index file (reference: reload() returns false) */
+    NS_ERR_FORMAT = 4,       /* posting list not strictly increasing in docId, docId >= N, offset misaligned */
+    NS_ERR_NOMEM = 5,
+    NS_ERR_STATE = 6         /* e.g. search before commit */
+} ns_status;
+
+#define NS_MAX_K 100          /* reference clamps k to 1..100: src/api_engine.cpp:377 */
+#define NS_MAX_TERMS 64       /* per (query, segment); reference expansion cap is 40: src/api_engine.cpp:417 */
+#define NS_BARREL_COUNT 64    /* include/barrels.hpp:12 */
+
+/* thread-local text of the last error raised on this thread */
+const char* ns_last_error(void);
+
+/* ------------------------------------------------------------------ */
+/* Device index (one GPU).  Replaces Segment{docs, lex, inv_barrels}   */
+/* (include/api_types.hpp:46-60) for the scoring loop.                 */
+/* ------------------------------------------------------------------ */
+typedef struct ns_index ns_index;
+
+/* One weighted query term resolved against one segment's lexicon
+ * (reference: the (term, qweight) pair of src/api_engine.cpp:449-461 after
+ * seg.lex.find(term) and bm25_idf(seg.N, e.df)). */
+typedef struct ns_qterm {
+    uint32_t seg;      /* global segment index (position in seg_names) */
+    uint32_t row;      /* CSR row of the term inside that segment, as uploaded */
+    float    idf;      /* bm25_idf(N, df), computed on the host (src/api_engine.cpp:45-47) */
+    float    weight;   /* qweight; 1.0f when semantic expansion is off (src/api_engine.cpp:420) */
+} ns_qterm;
+
+/* Hit{s, segId, docId} of src/api_engine.cpp:427-431 */
+typedef struct ns_hit {
+    float    score;
+    uint32_t seg;
+    uint32_t doc;
+} ns_hit;
+
+int ns_device_count(void);
+
+int ns_index_create(int device, ns_index** out);
+void ns_index_destroy(ns_index* idx);
+
+/* Stage one segment for the next commit.
+ *   doc_len[N]          DocInfo.doc_len (include/api_types.hpp:18-21)
+ *   term_begin[T]       first posting of row t, in postings (not bytes)
+ *   term_count[T]       LexEntry.count (include/api_types.hpp:23-29)
+ *   postings[P]         interleaved little-endian {u32 docId, u32 tf} exactly as in
+ *                       inverted_bNNN.bin (include/segment_writer.hpp:151-155)
+ * Validates: docId < N and strictly increasing inside every row. */
+int ns_index_add_segment(ns_index* idx, uint32_t global_seg, uint32_t N, float avgdl,
+                         const uint32_t* doc_len, uint32_t T, const uint64_t* term_begin,
+                         const uint32_t* term_count, const void* postings, uint64_t P);
+
+/* Atomically replace the searchable index with the staged segments
+ * (reference: `segments = std::move(loaded)` src/api_engine.cpp:90).  In-flight
+ * batches keep the index they started with.  On failure the previous index stays. */
+int ns_index_commit(ns_index* idx);
+/* Drop staged, uncommitted segments. */
+int ns_index_abort(ns_index* idx);
+
+int ns_index_num_segments(const ns_index* idx);
+uint64_t ns_index_device_bytes(const ns_index* idx);
+
+/* ------------------------------------------------------------------ */
+/* Batched search.                                                     */
+/* ------------------------------------------------------------------ */
+
+/* One-shot, HOST buffers in and out (the e2e path; H2D + kernels + D2H inside).
+ *   q_off[Q+1]   prefix offsets into terms[]; terms of one query are ordered by
+ *                (seg asc, then query-term order); duplicates are kept
+ *                (src/api_engine.cpp:391-397).
+ *   k            clamped to 1..100 like src/api_engine.cpp:377
+ *   out_hits     [Q][k_clamped] best first;  out_nhits[Q];  out_found[Q]
+ *                (found = Σ_segments |{docs with ≥1 matching posting}|, src/api_engine.cpp:495)
+ * Thread-safe: may be called concurrently from many host threads. */
+int ns_search_batch(ns_index* idx, uint32_t Q, int k, const uint64_t* q_off, const ns_qterm* terms,
+                    ns_hit* out_hits, uint32_t* out_nhits, uint64_t* out_found);
+
+/* Split form of the same call: prepare uploads the descriptors (H2D) and
+ * allocates device outputs; launch enqueues the kernels on `stream`
+ * (a cudaStream_t passed as void*, NULL = the batch's own stream); fetch copies
+ * results back and synchronises.  bench.py's device-resident `value` times
+ * ns_batch_launch alone. */
+typedef struct ns_batch ns_batch;
+int ns_batch_prepare(ns_index* idx, uint32_t Q, int k, const uint64_t* q_off, const ns_qterm* terms,
+                     ns_batch** out);
+int ns_batch_launch(ns_batch* b, void* stream);
+int ns_batch_sync(ns_batch* b);
+int ns_batch_fetch(ns_batch* b, ns_hit* out_hits, uint32_t* out_nhits, uint64_t* out_found);
+void ns_batch_destroy(ns_batch* b);
+/* device pointers of a batch's results ([Q][k] ns_hit, [Q] u32, [Q] u64) for
+ * torch.distributed all_gather without a host round trip */
+int ns_batch_device_results(ns_batch* b, void** d_hits, void** d_nhits, void** d_found);
+/* introspection for bench.py */
+uint64_t ns_batch_posting_count(const ns_batch* b);   /* Σ LexEntry.count over all (query, term, segment) */
+uint32_t ns_batch_num_launches(const ns_batch* b);    /* kernels one ns_batch_launch enqueues */
+float ns_batch_last_kernel_ms(ns_batch* b, int which); /* CUDA-event time of the last launch: 0 = score+topk, 1 = merge */
+int ns_batch_set_splits(ns_batch* b, uint32_t splits); /* 0 = auto */
+
+/* Merge `nlists` per-rank (or per-split) result sets on the device.
+ *   d_hits   [nlists][Q][k] ns_hit, each list best-first; d_nhits [nlists][Q]; d_found [nlists][Q]
+ *   outputs  [Q][k], [Q], [Q]  (device pointers)
+ * Order: score desc, seg asc, doc asc. */
+int ns_merge_device(int device, uint32_t Q, int k, uint32_t nlists, const void* d_hits,
+                    const void* d_nhits, const void* d_found, void* d_out_hits, void* d_out_nhits,
+                    void* d_out_found, void* stream);
+
+/* ------------------------------------------------------------------ */
+/* Engine mirror (host).  Same surface as cord19::Engine for this path.*/
+/* ------------------------------------------------------------------ */
+typedef struct ns_engine ns_engine;
+
+/* device < 0: host-only engine (lexicon / tokeniser / resolve available, search fails loudly) */
+int ns_engine_create(const char* index_dir, int device, ns_engine** out);
+void ns_engine_destroy(ns_engine* e);
+
+/* Shard selection for multi-GPU: this engine uploads only segments with
+ * (global_seg % world) == rank; set before reload.  Default world=1. */
+int ns_engine_set_shard(ns_engine* e, int rank, int world);
+
+/* Engine::reload (src/api_engine.cpp:50-90): manifest.bin or sorted scan of
+ * segments/seg_*, load every segment, upload, commit.  NS_ERR_IO if any file is missing. */
+int ns_engine_reload(ns_engine* e);
+
+int ns_engine_num_segments(const ns_engine* e);
+/* copies seg_names[i] into buf; returns length or -1 */
+int ns_engine_segment_name(const ns_engine* e, int i, char* buf, size_t cap);
+int ns_engine_segment_stats(const ns_engine* e, int i, uint32_t* N, float* avgdl, uint32_t* T, uint64_t* P);
+/* df / count of `term` in segment i; returns 0 and sets *df=*count=0 if absent */
+int ns_engine_term_stats(const ns_engine* e, int i, const char* term, uint32_t* df, uint32_t* count);
+
+/* Engine::search (src/api_engine.cpp:369-542) minus the LRU cache and the
+ * metadata.csv decoration: returns the reference's JSON object as text
+ * (keys: query, k, segments, results[{score, segment, docId, cord_uid}], found).
+ * Writes at most cap-1 bytes + NUL; returns the full length needed (like snprintf)
+ * in *needed. */
+int ns_engine_search_json(ns_engine* e, const char* query, int k, char* buf, size_t cap, size_t* needed);
+
+/* Batched form: `queries` is Q NUL-terminated strings.  has_found[q] = 0 when the
+ * reference would omit "found" (no usable terms: src/api_engine.cpp:407). */
+int ns_engine_search_batch(ns_engine* e, uint32_t Q, const char* const* queries, int k,
+                           ns_hit* out_hits, uint32_t* out_nhits, uint64_t* out_found,
+                           uint8_t* has_found);
+
+/* Front end only: tokenise + filter + lexicon lookup + IDF for a batch, producing
+ * the arrays ns_search_batch takes.  Two-call protocol: pass terms=NULL to get
+ * the count in *n_terms.  Only segments owned by this engine's shard are emitted. */
+int ns_engine_resolve_batch(ns_engine* e, uint32_t Q, const char* const* queries,
+                            uint64_t* q_off, ns_qterm* terms, uint64_t terms_cap, uint64_t* n_terms,
+                            uint8_t* has_terms);
+ns_index* ns_engine_index(ns_engine* e);
+/* cord_uid of (segment, doc); returns length or -1 */
+int ns_engine_cord_uid(const ns_engine* e, uint32_t seg, uint32_t doc, char* buf, size_t cap);
+
+/* ------------------------------------------------------------------ */
+/* Text + synthetic corpus tooling.                                    */
+/* ------------------------------------------------------------------ */
+
+/* tokenize + (len<2 | stopword) filter (include/textutil.hpp:13-37,
+ * src/api_engine.cpp:391-397).  Tokens are written NUL-separated into buf;
+ * returns the number of kept tokens, or -1 if buf is too small. */
+int ns_text_query_terms(const char* query, char* buf, size_t cap);
+
+typedef struct ns_corpus_spec {
+    uint64_t seed;        /* corpus seed (20260101) */
+    uint32_t vocab;       /* V */
+    double   zipf_s;      /* 1.0 */
+    double   zipf_q;      /* 25.0 : p(r) ∝ 1/(r+q)^s, r = 1..V */
+    uint32_t len_lo;      /* doc length L ~ U[len_lo, len_hi) */
+    uint32_t len_hi;
+} ns_corpus_spec;
+
+/* Generate docs [doc_base, doc_base+ndocs) of the synthetic corpus and write them as
+ * one segment directory in the reference's barrelized on-disk format
+ * (include/segment_writer.hpp:65-168).  write_forward!=0 also emits forward.bin and
+ * terms.bin (not read at query time).  dump_path!=NULL additionally writes the
+ * documents as a flat binary dump that oracle/ref_driver feeds to the reference's own
+ * SegmentWriter for byte-for-byte comparison. */
+int ns_corpus_write_segment(const ns_corpus_spec* spec, uint64_t doc_base, uint32_t ndocs,
+                            const char* segdir, int write_forward, const char* dump_path, int nthreads);
+/* manifest.bin (src/api_segment.cpp:29-35) */
+int ns_corpus_write_manifest(const char* index_dir, uint32_t nseg, const char* const* names);
+/* Deterministic query strings: query i has 1..max_terms terms "t<rank>" drawn from the
+ * corpus distribution.  head_ranks>0 forces the first term's rank into [1, head_ranks]
+ * (the high-df stress of BASELINE configs[3]).  Output: NUL-separated strings. */
+int ns_corpus_make_queries(const ns_corpus_spec* spec, uint64_t query_seed, uint32_t nq,
+                           uint32_t min_terms, uint32_t max_terms, uint32_t head_ranks,
+                           char* buf, size_t cap, size_t* needed);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NEXTSEARCH_B200_H */

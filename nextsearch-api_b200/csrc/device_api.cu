@@ -1,0 +1,662 @@
+// C-ABI implementation of the device path: ns_index_*, ns_batch_*, ns_search_batch, ns_merge_device.
+// Host-side glue only; all arithmetic on postings happens in bm25_kernels.cuh.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <numeric>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/nextsearch_b200.h"
+#include "bm25_kernels.cuh"
+#include "host/common.hpp"
+
+using namespace nsb;
+
+namespace {
+
+#define NS_CUDA(expr)                                                                          \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            set_error(std::string("CUDA error: ") + cudaGetErrorString(_e) + " at " #expr);    \
+            return NS_ERR_CUDA;                                                                \
+        }                                                                                      \
+    } while (0)
+
+constexpr size_t kAlign = 256;
+inline size_t align_up(size_t x) { return (x + kAlign - 1) / kAlign * kAlign; }
+
+// BM25 constants of src/api_engine.cpp:375-376, evaluated in f32 like the reference does
+const float kK1 = 1.2f;
+const float kB = 0.75f;
+
+struct SegState {
+    uint32_t gseg = 0, ndocs = 0, T = 0, ntiles = 0;
+    uint64_t P = 0;
+    float avgdl = 0.f;
+    uint2* d_post = nullptr;
+    float* d_norm = nullptr;
+    uint32_t* d_tileoff = nullptr;
+    std::vector<uint32_t> h_count;  // LexEntry.count per row (query weights, row validation)
+    uint64_t bytes = 0;
+    void release() {
+        if (d_post) cudaFree(d_post);
+        if (d_norm) cudaFree(d_norm);
+        if (d_tileoff) cudaFree(d_tileoff);
+        d_post = nullptr;
+        d_norm = nullptr;
+        d_tileoff = nullptr;
+    }
+};
+
+struct IndexState {
+    int device = 0;
+    uint32_t tile_docs = 8192;
+    std::vector<SegState> segs;  // ascending gseg
+    std::unordered_map<uint32_t, uint32_t> slot_of;
+    DevSeg* d_segs = nullptr;
+    uint32_t* d_tile_base = nullptr;
+    uint32_t total_tiles = 0;
+    uint64_t bytes = 0;
+    ~IndexState() {
+        cudaSetDevice(device);
+        for (auto& s : segs) s.release();
+        if (d_segs) cudaFree(d_segs);
+        if (d_tile_base) cudaFree(d_tile_base);
+    }
+};
+
+// Reusable per-call resources: one device blob, two pinned blobs, a stream and events.
+struct BatchRes {
+    int device = 0;
+    uint8_t* d_blob = nullptr;
+    size_t d_cap = 0;
+    uint8_t* h_in = nullptr;
+    size_t h_in_cap = 0;
+    uint8_t* h_out = nullptr;
+    size_t h_out_cap = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    ~BatchRes() {
+        cudaSetDevice(device);
+        if (d_blob) cudaFree(d_blob);
+        if (h_in) cudaFreeHost(h_in);
+        if (h_out) cudaFreeHost(h_out);
+        for (auto& e : ev)
+            if (e) cudaEventDestroy(e);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+}  // namespace
+
+struct ns_index {
+    int device = 0;
+    uint32_t tile_docs = 8192;
+    std::mutex mu;
+    std::shared_ptr<IndexState> live;
+    std::vector<SegState> staged;
+    std::vector<std::unique_ptr<BatchRes>> pool;
+    int sm_count = 148;
+};
+
+struct ns_batch {
+    ns_index* owner = nullptr;
+    std::shared_ptr<IndexState> st;
+    std::unique_ptr<BatchRes> res;
+    uint32_t Q = 0, k = 0, S = 1;
+    uint64_t nterms = 0, postings = 0;
+    // device sub-arrays
+    uint32_t* d_qoff = nullptr;
+    DevTerm* d_terms = nullptr;
+    uint32_t* d_order = nullptr;
+    uint8_t* d_out = nullptr;  // hits | nhits | found, contiguous == h_out layout
+    ns_hit* d_out_hits = nullptr;
+    uint32_t* d_out_n = nullptr;
+    unsigned long long* d_out_found = nullptr;
+    size_t out_bytes = 0, off_n = 0, off_found = 0;
+    // partial (split) results, allocated on demand
+    uint8_t* d_part = nullptr;
+    size_t d_part_cap = 0;
+    bool launched = false, has_merge = false;
+};
+
+extern "C" const char* ns_last_error(void) { return last_error(); }
+
+extern "C" int ns_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+extern "C" int ns_index_create(int device, ns_index** out) {
+    if (!out) { set_error("ns_index_create: out is null"); return NS_ERR_INVALID; }
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        set_error(std::string("no CUDA device available (") + cudaGetErrorString(e) +
+                  "); this library has no CPU fallback");
+        return NS_ERR_CUDA;
+    }
+    if (device < 0 || device >= n) { set_error("ns_index_create: device out of range"); return NS_ERR_INVALID; }
+    NS_CUDA(cudaSetDevice(device));
+    auto* idx = new ns_index();
+    idx->device = device;
+    cudaDeviceProp prop;
+    NS_CUDA(cudaGetDeviceProperties(&prop, device));
+    idx->sm_count = prop.multiProcessorCount;
+    if (const char* t = std::getenv("NSB200_TILE_DOCS")) {
+        int v = std::atoi(t);
+        if (v == 4096 || v == 8192 || v == 16384) idx->tile_docs = (uint32_t)v;
+    }
+    *out = idx;
+    return NS_OK;
+}
+
+extern "C" void ns_index_destroy(ns_index* idx) {
+    if (!idx) return;
+    cudaSetDevice(idx->device);
+    for (auto& s : idx->staged) s.release();
+    idx->pool.clear();
+    idx->live.reset();
+    delete idx;
+}
+
+extern "C" int ns_index_add_segment(ns_index* idx, uint32_t global_seg, uint32_t N, float avgdl,
+                                    const uint32_t* doc_len, uint32_t T, const uint64_t* term_begin,
+                                    const uint32_t* term_count, const void* postings, uint64_t P) {
+    if (!idx || (N && !doc_len) || (T && (!term_begin || !term_count)) || (P && !postings)) {
+        set_error("ns_index_add_segment: null argument");
+        return NS_ERR_INVALID;
+    }
+    if (P >= 0xFFFFFFFFull) { set_error("segment has >= 2^32 postings; split it"); return NS_ERR_INVALID; }
+    std::vector<uint32_t> begin32(T);
+    for (uint32_t t = 0; t < T; t++) {
+        if (term_begin[t] + term_count[t] > P) {
+            set_error("ns_index_add_segment: row " + std::to_string(t) + " exceeds the posting array");
+            return NS_ERR_FORMAT;
+        }
+        begin32[t] = (uint32_t)term_begin[t];
+    }
+    NS_CUDA(cudaSetDevice(idx->device));
+    SegState s;
+    s.gseg = global_seg;
+    s.ndocs = N;
+    s.T = T;
+    s.P = P;
+    s.avgdl = avgdl;
+    s.ntiles = (N + idx->tile_docs - 1) / idx->tile_docs;
+    if (s.ntiles == 0) s.ntiles = 1;
+    s.h_count.assign(term_count, term_count + T);
+
+    uint32_t *d_len = nullptr, *d_begin = nullptr, *d_count = nullptr;
+    unsigned int* d_err = nullptr;
+    auto cleanup = [&]() {
+        if (d_len) cudaFree(d_len);
+        if (d_begin) cudaFree(d_begin);
+        if (d_count) cudaFree(d_count);
+        if (d_err) cudaFree(d_err);
+    };
+#define NS_CUDA_SEG(expr)                                                                       \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess) {                                                                \
+            set_error(std::string("CUDA error: ") + cudaGetErrorString(_e) + " at " #expr);     \
+            cleanup();                                                                          \
+            s.release();                                                                        \
+            return NS_ERR_CUDA;                                                                 \
+        }                                                                                       \
+    } while (0)
+
+    const size_t tile_entries = (size_t)T * (s.ntiles + 1);
+    NS_CUDA_SEG(cudaMalloc(&s.d_post, std::max<size_t>(16, P * sizeof(uint2))));
+    NS_CUDA_SEG(cudaMalloc(&s.d_norm, std::max<size_t>(16, (size_t)N * sizeof(float))));
+    NS_CUDA_SEG(cudaMalloc(&s.d_tileoff, std::max<size_t>(16, tile_entries * sizeof(uint32_t))));
+    NS_CUDA_SEG(cudaMalloc(&d_len, std::max<size_t>(16, (size_t)N * 4)));
+    NS_CUDA_SEG(cudaMalloc(&d_begin, std::max<size_t>(16, (size_t)T * 4)));
+    NS_CUDA_SEG(cudaMalloc(&d_count, std::max<size_t>(16, (size_t)T * 4)));
+    NS_CUDA_SEG(cudaMalloc(&d_err, sizeof(unsigned int)));
+    NS_CUDA_SEG(cudaMemset(d_err, 0, sizeof(unsigned int)));
+    if (P) NS_CUDA_SEG(cudaMemcpy(s.d_post, postings, P * sizeof(uint2), cudaMemcpyHostToDevice));
+    if (N) NS_CUDA_SEG(cudaMemcpy(d_len, doc_len, (size_t)N * 4, cudaMemcpyHostToDevice));
+    if (T) {
+        NS_CUDA_SEG(cudaMemcpy(d_begin, begin32.data(), (size_t)T * 4, cudaMemcpyHostToDevice));
+        NS_CUDA_SEG(cudaMemcpy(d_count, term_count, (size_t)T * 4, cudaMemcpyHostToDevice));
+    }
+    if (N) {
+        doc_norm_kernel<<<(N + 255) / 256, 256>>>(d_len, s.d_norm, N, avgdl, kK1, kB);
+        NS_CUDA_SEG(cudaGetLastError());
+    }
+    if (T) {
+        const int blocks = (int)std::min<uint64_t>(((uint64_t)T + 7) / 8, (uint64_t)idx->sm_count * 32);
+        validate_rows_kernel<<<blocks, 256>>>(s.d_post, d_begin, d_count, T, N, d_err);
+        NS_CUDA_SEG(cudaGetLastError());
+        const uint64_t tb = (tile_entries + 255) / 256;
+        tile_table_kernel<<<(int)std::min<uint64_t>(tb, (uint64_t)idx->sm_count * 64), 256>>>(
+            s.d_post, d_begin, d_count, T, s.ntiles, idx->tile_docs, s.d_tileoff);
+        NS_CUDA_SEG(cudaGetLastError());
+    }
+    unsigned int h_err = 0;
+    NS_CUDA_SEG(cudaMemcpy(&h_err, d_err, sizeof(h_err), cudaMemcpyDeviceToHost));
+    NS_CUDA_SEG(cudaDeviceSynchronize());
+    cleanup();
+#undef NS_CUDA_SEG
+    if (h_err) {
+        s.release();
+        set_error("segment " + std::to_string(global_seg) + ": " + std::to_string(h_err) +
+                  " postings are out of order, duplicated or have docId >= N");
+        return NS_ERR_FORMAT;
+    }
+    s.bytes = P * sizeof(uint2) + (uint64_t)N * 4 + tile_entries * 4;
+    std::lock_guard<std::mutex> lk(idx->mu);
+    for (auto& o : idx->staged) {
+        if (o.gseg == global_seg) {
+            s.release();
+            set_error("segment " + std::to_string(global_seg) + " staged twice");
+            return NS_ERR_INVALID;
+        }
+    }
+    idx->staged.push_back(std::move(s));
+    return NS_OK;
+}
+
+extern "C" int ns_index_abort(ns_index* idx) {
+    if (!idx) return NS_ERR_INVALID;
+    cudaSetDevice(idx->device);
+    std::lock_guard<std::mutex> lk(idx->mu);
+    for (auto& s : idx->staged) s.release();
+    idx->staged.clear();
+    return NS_OK;
+}
+
+extern "C" int ns_index_commit(ns_index* idx) {
+    if (!idx) { set_error("ns_index_commit: null"); return NS_ERR_INVALID; }
+    NS_CUDA(cudaSetDevice(idx->device));
+    std::lock_guard<std::mutex> lk(idx->mu);
+    auto st = std::make_shared<IndexState>();
+    st->device = idx->device;
+    st->tile_docs = idx->tile_docs;
+    std::sort(idx->staged.begin(), idx->staged.end(), [](const SegState& a, const SegState& b) { return a.gseg < b.gseg; });
+    std::vector<DevSeg> h_segs;
+    std::vector<uint32_t> h_base(1, 0);
+    for (auto& s : idx->staged) {
+        DevSeg d;
+        d.post = s.d_post;
+        d.norm = s.d_norm;
+        d.tileoff = s.d_tileoff;
+        d.ndocs = s.ndocs;
+        d.T = s.T;
+        d.ntiles = s.ntiles;
+        d.gseg = s.gseg;
+        h_segs.push_back(d);
+        h_base.push_back(h_base.back() + s.ntiles);
+        st->bytes += s.bytes;
+    }
+    const size_t nseg = h_segs.size();
+    cudaError_t e = cudaMalloc(&st->d_segs, std::max<size_t>(16, nseg * sizeof(DevSeg)));
+    if (e == cudaSuccess) e = cudaMalloc(&st->d_tile_base, (nseg + 1) * sizeof(uint32_t));
+    if (e == cudaSuccess && nseg) e = cudaMemcpy(st->d_segs, h_segs.data(), nseg * sizeof(DevSeg), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(st->d_tile_base, h_base.data(), (nseg + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        // st's destructor frees what was allocated; staged segments stay staged, live index untouched
+        set_error(std::string("CUDA error in ns_index_commit: ") + cudaGetErrorString(e));
+        return NS_ERR_CUDA;
+    }
+    st->total_tiles = h_base.back();
+    st->segs = std::move(idx->staged);
+    idx->staged.clear();
+    for (uint32_t i = 0; i < st->segs.size(); i++) st->slot_of[st->segs[i].gseg] = i;
+    idx->live = st;  // in-flight batches keep their own shared_ptr to the old state
+    return NS_OK;
+}
+
+extern "C" int ns_index_num_segments(const ns_index* idx) {
+    if (!idx) return 0;
+    auto* m = const_cast<ns_index*>(idx);
+    std::lock_guard<std::mutex> lk(m->mu);
+    return m->live ? (int)m->live->segs.size() : 0;
+}
+
+extern "C" uint64_t ns_index_device_bytes(const ns_index* idx) {
+    if (!idx) return 0;
+    auto* m = const_cast<ns_index*>(idx);
+    std::lock_guard<std::mutex> lk(m->mu);
+    return m->live ? m->live->bytes : 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+
+namespace {
+
+int acquire_res(ns_index* idx, size_t d_need, size_t in_need, size_t out_need, std::unique_ptr<BatchRes>& out) {
+    {
+        std::lock_guard<std::mutex> lk(idx->mu);
+        for (size_t i = 0; i < idx->pool.size(); i++) {
+            auto& r = idx->pool[i];
+            if (r->d_cap >= d_need && r->h_in_cap >= in_need && r->h_out_cap >= out_need) {
+                out = std::move(r);
+                idx->pool.erase(idx->pool.begin() + i);
+                return NS_OK;
+            }
+        }
+    }
+    auto r = std::make_unique<BatchRes>();
+    r->device = idx->device;
+    // round capacities up so that a stream of similar batches reuses one resource set
+    auto grow = [](size_t n) { size_t c = 1 << 16; while (c < n) c <<= 1; return c; };
+    r->d_cap = grow(d_need);
+    r->h_in_cap = grow(in_need);
+    r->h_out_cap = grow(out_need);
+    NS_CUDA(cudaMalloc(&r->d_blob, r->d_cap));
+    NS_CUDA(cudaMallocHost(&r->h_in, r->h_in_cap));
+    NS_CUDA(cudaMallocHost(&r->h_out, r->h_out_cap));
+    NS_CUDA(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
+    for (auto& e : r->ev) NS_CUDA(cudaEventCreate(&e));
+    out = std::move(r);
+    return NS_OK;
+}
+
+uint32_t auto_splits(const ns_index* idx, const IndexState& st, uint32_t Q) {
+    if (const char* s = std::getenv("NSB200_SPLITS")) {
+        int v = std::atoi(s);
+        if (v > 0) return std::min<uint32_t>((uint32_t)v, std::max<uint32_t>(1, st.total_tiles));
+    }
+    // enough CTAs for ~2 waves at 6 CTAs/SM
+    const uint32_t target = (uint32_t)idx->sm_count * 12;
+    if (Q >= target) return 1;
+    uint32_t s = (target + Q - 1) / std::max<uint32_t>(1, Q);
+    s = std::min<uint32_t>(s, std::max<uint32_t>(1, st.total_tiles));
+    s = std::min<uint32_t>(s, (uint32_t)kMergeMaxLists);
+    return std::max<uint32_t>(1, s);
+}
+
+template <int TD>
+cudaError_t launch_score(const ScoreArgs& a, cudaStream_t s) {
+    const size_t smem = (size_t)TD * sizeof(float);
+    if (smem > 48 * 1024) {  // per device, cheap: set on every launch
+        cudaError_t e = cudaFuncSetAttribute(bm25_score_topk_kernel<TD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    bm25_score_topk_kernel<TD><<<a.Q * a.S, kThreads, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+extern "C" int ns_batch_prepare(ns_index* idx, uint32_t Q, int k_in, const uint64_t* q_off, const ns_qterm* terms,
+                                ns_batch** out) {
+    if (!idx || !out || !q_off || (Q && q_off[Q] && !terms)) { set_error("ns_batch_prepare: null argument"); return NS_ERR_INVALID; }
+    *out = nullptr;
+    std::shared_ptr<IndexState> st;
+    {
+        std::lock_guard<std::mutex> lk(idx->mu);
+        st = idx->live;
+    }
+    if (!st) { set_error("ns_batch_prepare: index has no committed segments"); return NS_ERR_STATE; }
+    NS_CUDA(cudaSetDevice(idx->device));
+    const uint32_t k = (uint32_t)std::max(1, std::min(k_in, NS_MAX_K));  // src/api_engine.cpp:377
+
+    // ---- host pass: keep the terms of segments this index holds, validate, weigh queries ----
+    const uint64_t nin = q_off[Q];
+    std::vector<DevTerm> kept;
+    kept.reserve(nin);
+    std::vector<uint32_t> qoff32((size_t)Q + 1, 0);
+    std::vector<uint64_t> weight(Q, 0);
+    uint64_t total_post = 0;
+    for (uint32_t q = 0; q < Q; q++) {
+        if (q_off[q + 1] < q_off[q]) { set_error("ns_batch_prepare: q_off not monotone"); return NS_ERR_INVALID; }
+        uint32_t prev_slot = 0, in_seg = 0;
+        bool have_prev = false;
+        for (uint64_t e = q_off[q]; e < q_off[q + 1]; e++) {
+            const ns_qterm& t = terms[e];
+            auto it = st->slot_of.find(t.seg);
+            if (it == st->slot_of.end()) continue;  // another rank's segment
+            const uint32_t slot = it->second;
+            const SegState& sg = st->segs[slot];
+            if (t.row >= sg.T) { set_error("ns_batch_prepare: row out of range"); return NS_ERR_INVALID; }
+            if (have_prev && slot < prev_slot) { set_error("ns_batch_prepare: terms of a query must be ordered by segment"); return NS_ERR_INVALID; }
+            if (!have_prev || slot != prev_slot) in_seg = 0;
+            have_prev = true;
+            prev_slot = slot;
+            const uint32_t cnt = sg.h_count[t.row];
+            if (cnt == 0) continue;
+            if (++in_seg > NS_MAX_TERMS) { set_error("ns_batch_prepare: more than NS_MAX_TERMS terms for one (query, segment)"); return NS_ERR_INVALID; }
+            kept.push_back(DevTerm{slot, t.row, t.idf, t.weight});
+            weight[q] += cnt;
+        }
+        if (kept.size() > 0xFFFFFFF0ull) { set_error("ns_batch_prepare: too many terms"); return NS_ERR_INVALID; }
+        qoff32[q + 1] = (uint32_t)kept.size();
+        total_post += weight[q];
+    }
+    std::vector<uint32_t> order(Q);
+    std::iota(order.begin(), order.end(), 0u);
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return weight[a] > weight[b]; });
+
+    auto b = std::make_unique<ns_batch>();
+    b->owner = idx;
+    b->st = st;
+    b->Q = Q;
+    b->k = k;
+    b->nterms = kept.size();
+    b->postings = total_post;
+    b->S = auto_splits(idx, *st, Q);
+
+    const size_t sz_qoff = align_up(((size_t)Q + 1) * 4);
+    const size_t sz_terms = align_up(std::max<size_t>(1, kept.size()) * sizeof(DevTerm));
+    const size_t sz_order = align_up(std::max<size_t>(1, Q) * 4);
+    const size_t in_bytes = sz_qoff + sz_terms + sz_order;
+    const size_t sz_hits = align_up(std::max<size_t>(1, (size_t)Q * k) * sizeof(ns_hit));
+    const size_t sz_n = align_up(std::max<size_t>(1, Q) * 4);
+    const size_t sz_found = align_up(std::max<size_t>(1, Q) * 8);
+    b->out_bytes = sz_hits + sz_n + sz_found;
+    b->off_n = sz_hits;
+    b->off_found = sz_hits + sz_n;
+
+    int rc = acquire_res(idx, in_bytes + b->out_bytes, in_bytes, b->out_bytes, b->res);
+    if (rc != NS_OK) return rc;
+    BatchRes& r = *b->res;
+    std::memcpy(r.h_in, qoff32.data(), ((size_t)Q + 1) * 4);
+    if (!kept.empty()) std::memcpy(r.h_in + sz_qoff, kept.data(), kept.size() * sizeof(DevTerm));
+    if (Q) std::memcpy(r.h_in + sz_qoff + sz_terms, order.data(), (size_t)Q * 4);
+    b->d_qoff = reinterpret_cast<uint32_t*>(r.d_blob);
+    b->d_terms = reinterpret_cast<DevTerm*>(r.d_blob + sz_qoff);
+    b->d_order = reinterpret_cast<uint32_t*>(r.d_blob + sz_qoff + sz_terms);
+    b->d_out = r.d_blob + in_bytes;
+    b->d_out_hits = reinterpret_cast<ns_hit*>(b->d_out);
+    b->d_out_n = reinterpret_cast<uint32_t*>(b->d_out + b->off_n);
+    b->d_out_found = reinterpret_cast<unsigned long long*>(b->d_out + b->off_found);
+    NS_CUDA(cudaMemcpyAsync(r.d_blob, r.h_in, in_bytes, cudaMemcpyHostToDevice, r.stream));
+    NS_CUDA(cudaStreamSynchronize(r.stream));
+    *out = b.release();
+    return NS_OK;
+}
+
+static int ensure_part(ns_batch* b) {
+    if (b->S <= 1) return NS_OK;
+    const size_t lists = (size_t)b->Q * b->S;
+    const size_t need = align_up(lists * b->k * sizeof(ns_hit)) + align_up(lists * 4) + align_up(lists * 8);
+    if (b->d_part_cap >= need) return NS_OK;
+    if (b->d_part) cudaFree(b->d_part);
+    b->d_part = nullptr;
+    b->d_part_cap = 0;
+    NS_CUDA(cudaMalloc(&b->d_part, need));
+    b->d_part_cap = need;
+    return NS_OK;
+}
+
+extern "C" int ns_batch_set_splits(ns_batch* b, uint32_t splits) {
+    if (!b) return NS_ERR_INVALID;
+    if (splits == 0) splits = auto_splits(b->owner, *b->st, b->Q);
+    splits = std::min<uint32_t>(splits, std::max<uint32_t>(1, b->st->total_tiles));
+    splits = std::min<uint32_t>(splits, (uint32_t)kMergeMaxLists);
+    b->S = std::max<uint32_t>(1, splits);
+    return NS_OK;
+}
+
+extern "C" int ns_batch_launch(ns_batch* b, void* stream) {
+    if (!b) { set_error("ns_batch_launch: null"); return NS_ERR_INVALID; }
+    NS_CUDA(cudaSetDevice(b->st->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : b->res->stream;
+    int rc = ensure_part(b);
+    if (rc != NS_OK) return rc;
+    b->has_merge = b->S > 1;
+    NS_CUDA(cudaEventRecord(b->res->ev[0], s));
+    if (b->Q > 0) {
+        ScoreArgs a;
+        a.segs = b->st->d_segs;
+        a.tile_base = b->st->d_tile_base;
+        a.nseg = (uint32_t)b->st->segs.size();
+        a.total_tiles = b->st->total_tiles;
+        a.qoff = b->d_qoff;
+        a.terms = b->d_terms;
+        a.order = b->d_order;
+        a.Q = b->Q;
+        a.k = b->k;
+        a.S = b->S;
+        a.k1p1 = kK1 + 1.0f;
+        const size_t lists = (size_t)b->Q * b->S;
+        if (b->S > 1) {
+            a.hits = reinterpret_cast<ns_hit*>(b->d_part);
+            a.nhits = reinterpret_cast<uint32_t*>(b->d_part + align_up(lists * b->k * sizeof(ns_hit)));
+            a.found = reinterpret_cast<unsigned long long*>(b->d_part + align_up(lists * b->k * sizeof(ns_hit)) + align_up(lists * 4));
+        } else {
+            a.hits = b->d_out_hits;
+            a.nhits = b->d_out_n;
+            a.found = b->d_out_found;
+        }
+        cudaError_t e;
+        switch (b->st->tile_docs) {
+            case 4096: e = launch_score<4096>(a, s); break;
+            case 16384: e = launch_score<16384>(a, s); break;
+            default: e = launch_score<8192>(a, s); break;
+        }
+        if (e != cudaSuccess) { set_error(std::string("score kernel launch failed: ") + cudaGetErrorString(e)); return NS_ERR_CUDA; }
+        NS_CUDA(cudaEventRecord(b->res->ev[1], s));
+        if (b->S > 1) {
+            MergeArgs m;
+            m.hits = a.hits;
+            m.nhits = a.nhits;
+            m.found = a.found;
+            m.ls = b->k;
+            m.qs = (uint64_t)b->S * b->k;
+            m.ls2 = 1;
+            m.qs2 = b->S;
+            m.Q = b->Q;
+            m.k = b->k;
+            m.nlists = b->S;
+            m.out_hits = b->d_out_hits;
+            m.out_nhits = b->d_out_n;
+            m.out_found = b->d_out_found;
+            const size_t smem = (size_t)kMergeWarps * b->S * sizeof(unsigned short);
+            topk_merge_kernel<<<(b->Q + kMergeWarps - 1) / kMergeWarps, kMergeWarps * 32, smem, s>>>(m);
+            NS_CUDA(cudaGetLastError());
+        }
+    } else {
+        NS_CUDA(cudaEventRecord(b->res->ev[1], s));
+    }
+    NS_CUDA(cudaEventRecord(b->res->ev[2], s));
+    b->launched = true;
+    return NS_OK;
+}
+
+extern "C" int ns_batch_sync(ns_batch* b) {
+    if (!b) return NS_ERR_INVALID;
+    NS_CUDA(cudaSetDevice(b->st->device));
+    if (b->launched) NS_CUDA(cudaEventSynchronize(b->res->ev[2]));
+    return NS_OK;
+}
+
+extern "C" int ns_batch_fetch(ns_batch* b, ns_hit* out_hits, uint32_t* out_nhits, uint64_t* out_found) {
+    if (!b || !b->launched) { set_error("ns_batch_fetch: batch was not launched"); return NS_ERR_STATE; }
+    NS_CUDA(cudaSetDevice(b->st->device));
+    BatchRes& r = *b->res;
+    // order the copy after the kernels even when they ran on a caller-supplied stream
+    NS_CUDA(cudaStreamWaitEvent(r.stream, r.ev[2], 0));
+    NS_CUDA(cudaMemcpyAsync(r.h_out, b->d_out, b->out_bytes, cudaMemcpyDeviceToHost, r.stream));
+    NS_CUDA(cudaStreamSynchronize(r.stream));
+    if (out_hits) std::memcpy(out_hits, r.h_out, (size_t)b->Q * b->k * sizeof(ns_hit));
+    if (out_nhits) std::memcpy(out_nhits, r.h_out + b->off_n, (size_t)b->Q * 4);
+    if (out_found) std::memcpy(out_found, r.h_out + b->off_found, (size_t)b->Q * 8);
+    return NS_OK;
+}
+
+extern "C" void ns_batch_destroy(ns_batch* b) {
+    if (!b) return;
+    cudaSetDevice(b->st->device);
+    if (b->launched) cudaEventSynchronize(b->res->ev[2]);
+    if (b->d_part) cudaFree(b->d_part);
+    if (b->owner && b->res) {
+        std::lock_guard<std::mutex> lk(b->owner->mu);
+        if (b->owner->pool.size() < 64) b->owner->pool.push_back(std::move(b->res));
+    }
+    delete b;
+}
+
+extern "C" int ns_batch_device_results(ns_batch* b, void** d_hits, void** d_nhits, void** d_found) {
+    if (!b) return NS_ERR_INVALID;
+    if (d_hits) *d_hits = b->d_out_hits;
+    if (d_nhits) *d_nhits = b->d_out_n;
+    if (d_found) *d_found = b->d_out_found;
+    return NS_OK;
+}
+
+extern "C" uint64_t ns_batch_posting_count(const ns_batch* b) { return b ? b->postings : 0; }
+extern "C" uint32_t ns_batch_num_launches(const ns_batch* b) { return b ? (b->Q == 0 ? 0u : (b->S > 1 ? 2u : 1u)) : 0u; }
+
+extern "C" float ns_batch_last_kernel_ms(ns_batch* b, int which) {
+    if (!b || !b->launched || which < 0 || which > 1) return -1.0f;
+    cudaSetDevice(b->st->device);
+    if (cudaEventSynchronize(b->res->ev[2]) != cudaSuccess) return -1.0f;
+    float ms = -1.0f;
+    if (cudaEventElapsedTime(&ms, b->res->ev[which], b->res->ev[which + 1]) != cudaSuccess) return -1.0f;
+    return ms;
+}
+
+extern "C" int ns_search_batch(ns_index* idx, uint32_t Q, int k, const uint64_t* q_off, const ns_qterm* terms,
+                               ns_hit* out_hits, uint32_t* out_nhits, uint64_t* out_found) {
+    ns_batch* b = nullptr;
+    int rc = ns_batch_prepare(idx, Q, k, q_off, terms, &b);
+    if (rc != NS_OK) return rc;
+    rc = ns_batch_launch(b, nullptr);
+    if (rc == NS_OK) rc = ns_batch_fetch(b, out_hits, out_nhits, out_found);
+    ns_batch_destroy(b);
+    return rc;
+}
+
+extern "C" int ns_merge_device(int device, uint32_t Q, int k_in, uint32_t nlists, const void* d_hits,
+                               const void* d_nhits, const void* d_found, void* d_out_hits, void* d_out_nhits,
+                               void* d_out_found, void* stream) {
+    if (!d_hits || !d_nhits || !d_found || !d_out_hits || !d_out_nhits || !d_out_found) {
+        set_error("ns_merge_device: null argument");
+        return NS_ERR_INVALID;
+    }
+    if (nlists == 0 || nlists > (uint32_t)kMergeMaxLists) { set_error("ns_merge_device: nlists out of range"); return NS_ERR_INVALID; }
+    NS_CUDA(cudaSetDevice(device));
+    const uint32_t k = (uint32_t)std::max(1, std::min(k_in, NS_MAX_K));
+    if (Q == 0) return NS_OK;
+    MergeArgs m;
+    m.hits = static_cast<const ns_hit*>(d_hits);
+    m.nhits = static_cast<const uint32_t*>(d_nhits);
+    m.found = static_cast<const unsigned long long*>(d_found);
+    m.ls = (uint64_t)Q * k;
+    m.qs = k;
+    m.ls2 = Q;
+    m.qs2 = 1;
+    m.Q = Q;
+    m.k = k;
+    m.nlists = nlists;
+    m.out_hits = static_cast<ns_hit*>(d_out_hits);
+    m.out_nhits = static_cast<uint32_t*>(d_out_nhits);
+    m.out_found = static_cast<unsigned long long*>(d_out_found);
+    const size_t smem = (size_t)kMergeWarps * nlists * sizeof(unsigned short);
+    topk_merge_kernel<<<(Q + kMergeWarps - 1) / kMergeWarps, kMergeWarps * 32, smem, (cudaStream_t)stream>>>(m);
+    NS_CUDA(cudaGetLastError());
+    return NS_OK;
+}

@@ -1,0 +1,50 @@
+// Query text front end: same token stream as the reference's include/textutil.hpp:13-37 plus the
+// filter of src/api_engine.cpp:391-397 (drop len<2 and stopwords, keep order and duplicates).
+#pragma once
+#include <string>
+#include <vector>
+
+namespace nsb {
+
+// ASCII [A-Za-z0-9]+ runs, lower-cased.  The reference calls std::isalnum/std::tolower in the
+// "C" locale, where only ASCII letters and digits qualify; bytes >= 0x80 separate tokens.
+inline void tokenize(const char* text, std::vector<std::string>& out) {
+    out.clear();
+    std::string cur;
+    for (const unsigned char* p = (const unsigned char*)text; *p; ++p) {
+        unsigned char c = *p;
+        bool digit = c >= '0' && c <= '9';
+        bool lower = c >= 'a' && c <= 'z';
+        bool upper = c >= 'A' && c <= 'Z';
+        if (digit || lower || upper) {
+            cur.push_back(upper ? (char)(c - 'A' + 'a') : (char)c);
+        } else if (!cur.empty()) {
+            out.push_back(cur);
+            cur.clear();
+        }
+    }
+    if (!cur.empty()) out.push_back(cur);
+}
+
+inline bool is_stopword(const std::string& t) {
+    // the 24 words of include/textutil.hpp:32-35; all have length 1..4
+    static const char* const sw[] = {"the", "a",  "an",  "and",  "or", "of",   "to", "in",   "for",  "on",   "with", "by",
+                                     "as",  "is", "are", "was",  "were", "be", "been", "it", "this", "that", "from", "at"};
+    if (t.size() > 4) return false;
+    for (const char* w : sw)
+        if (t == w) return true;
+    return false;
+}
+
+inline void query_terms(const char* query, std::vector<std::string>& out) {
+    std::vector<std::string> toks;
+    tokenize(query, toks);
+    out.clear();
+    for (auto& t : toks) {
+        if (t.size() < 2) continue;
+        if (is_stopword(t)) continue;
+        out.push_back(std::move(t));
+    }
+}
+
+}  // namespace nsb

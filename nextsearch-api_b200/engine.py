@@ -1,0 +1,317 @@
+"""Python mirror of the reference's search surface (cord19::Engine, include/api_engine.hpp:23-91)
+over the C ABI.  Names and argument meaning follow the reference: ``Engine.reload()`` returns a
+bool like Engine::reload (src/api_engine.cpp:50), ``Engine.search(query, k)`` returns the same
+JSON object as Engine::search (src/api_engine.cpp:369-542) minus cache flags and metadata.csv
+decoration.  All scoring happens in libnsb200.so on the GPU; this file only marshals buffers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+from dataclasses import dataclass
+from typing import Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import NS_MAX_K, check
+
+HIT_DTYPE = np.dtype([("score", "<f4"), ("seg", "<u4"), ("doc", "<u4")])
+QTERM_DTYPE = np.dtype([("seg", "<u4"), ("row", "<u4"), ("idf", "<f4"), ("weight", "<f4")])
+
+
+def clamp_k(k: int) -> int:
+    """K = max(1, min(k, 100)) — src/api_engine.cpp:377."""
+    return max(1, min(int(k), NS_MAX_K))
+
+
+def _cstr_array(strings: Sequence[str]):
+    arr = (C.c_char_p * max(1, len(strings)))()
+    for i, s in enumerate(strings):
+        arr[i] = s.encode("utf-8") if isinstance(s, str) else s
+    return arr
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+@dataclass
+class BatchResult:
+    hits: np.ndarray       # [Q, K] HIT_DTYPE, best first; entries >= nhits[q] are undefined
+    nhits: np.ndarray      # [Q] u32
+    found: np.ndarray      # [Q] u64
+    has_found: np.ndarray  # [Q] bool — False where the reference omits "found" (no usable terms)
+    k: int
+
+
+class Batch:
+    """ns_batch: descriptors resident on the device; launch() enqueues the kernels only."""
+
+    def __init__(self, index: "DeviceIndex", q_off: np.ndarray, terms: np.ndarray, k: int):
+        self._lib = _lib.load()
+        self.Q = int(len(q_off) - 1)
+        self.k = clamp_k(k)
+        q_off = np.ascontiguousarray(q_off, dtype=np.uint64)
+        terms = np.ascontiguousarray(terms, dtype=QTERM_DTYPE)
+        h = C.c_void_p()
+        check(self._lib.ns_batch_prepare(index._h, self.Q, int(k), _ptr(q_off), _ptr(terms), C.byref(h)))
+        self._h = h
+        self._index = index  # keep the index alive
+
+    def set_splits(self, splits: int) -> None:
+        check(self._lib.ns_batch_set_splits(self._h, int(splits)))
+
+    def launch(self, stream: Optional[int] = None) -> None:
+        check(self._lib.ns_batch_launch(self._h, C.c_void_p(stream) if stream else None))
+
+    def sync(self) -> None:
+        check(self._lib.ns_batch_sync(self._h))
+
+    def fetch(self) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        hits = np.zeros((self.Q, self.k), dtype=HIT_DTYPE)
+        nhits = np.zeros(self.Q, dtype=np.uint32)
+        found = np.zeros(self.Q, dtype=np.uint64)
+        check(self._lib.ns_batch_fetch(self._h, _ptr(hits), _ptr(nhits), _ptr(found)))
+        return hits, nhits, found
+
+    def device_results(self) -> Tuple[int, int, int]:
+        a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        check(self._lib.ns_batch_device_results(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    @property
+    def posting_count(self) -> int:
+        return int(self._lib.ns_batch_posting_count(self._h))
+
+    @property
+    def num_launches(self) -> int:
+        return int(self._lib.ns_batch_num_launches(self._h))
+
+    def kernel_ms(self, which: int = 0) -> float:
+        return float(self._lib.ns_batch_last_kernel_ms(self._h, which))
+
+    def close(self) -> None:
+        if self._h:
+            self._lib.ns_batch_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DeviceIndex:
+    """ns_index: the device-resident CSR form of the engine's segments on one GPU."""
+
+    def __init__(self, device: int = 0, _borrowed: Optional[int] = None, _owner=None):
+        self._lib = _lib.load()
+        self._owner = _owner
+        if _borrowed is not None:
+            self._h = C.c_void_p(_borrowed)
+            self._own = False
+        else:
+            h = C.c_void_p()
+            check(self._lib.ns_index_create(int(device), C.byref(h)))
+            self._h = h
+            self._own = True
+        self.device = device
+
+    def add_segment(self, global_seg: int, avgdl: float, doc_len: np.ndarray, term_begin: np.ndarray,
+                    term_count: np.ndarray, postings: np.ndarray) -> None:
+        doc_len = np.ascontiguousarray(doc_len, dtype=np.uint32)
+        term_begin = np.ascontiguousarray(term_begin, dtype=np.uint64)
+        term_count = np.ascontiguousarray(term_count, dtype=np.uint32)
+        postings = np.ascontiguousarray(postings, dtype=np.uint32).reshape(-1, 2)
+        check(self._lib.ns_index_add_segment(self._h, int(global_seg), len(doc_len), C.c_float(avgdl), _ptr(doc_len),
+                                             len(term_begin), _ptr(term_begin), _ptr(term_count), _ptr(postings),
+                                             postings.shape[0]))
+
+    def commit(self) -> None:
+        check(self._lib.ns_index_commit(self._h))
+
+    def abort(self) -> None:
+        check(self._lib.ns_index_abort(self._h))
+
+    @property
+    def num_segments(self) -> int:
+        return int(self._lib.ns_index_num_segments(self._h))
+
+    @property
+    def device_bytes(self) -> int:
+        return int(self._lib.ns_index_device_bytes(self._h))
+
+    def prepare(self, q_off: np.ndarray, terms: np.ndarray, k: int) -> Batch:
+        return Batch(self, q_off, terms, k)
+
+    def search_batch(self, q_off: np.ndarray, terms: np.ndarray, k: int):
+        """ns_search_batch: host buffers in, host buffers out (H2D + kernels + D2H)."""
+        Q = len(q_off) - 1
+        K = clamp_k(k)
+        q_off = np.ascontiguousarray(q_off, dtype=np.uint64)
+        terms = np.ascontiguousarray(terms, dtype=QTERM_DTYPE)
+        hits = np.zeros((Q, K), dtype=HIT_DTYPE)
+        nhits = np.zeros(Q, dtype=np.uint32)
+        found = np.zeros(Q, dtype=np.uint64)
+        check(self._lib.ns_search_batch(self._h, Q, int(k), _ptr(q_off), _ptr(terms), _ptr(hits), _ptr(nhits),
+                                        _ptr(found)))
+        return hits, nhits, found
+
+    def close(self) -> None:
+        if self._h and self._own:
+            self._lib.ns_index_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def merge_device(device: int, Q: int, k: int, nlists: int, d_hits: int, d_nhits: int, d_found: int, d_out_hits: int,
+                 d_out_nhits: int, d_out_found: int, stream: Optional[int] = None) -> None:
+    """ns_merge_device on raw device pointers ([nlists][Q][k] lists -> [Q][k])."""
+    lib = _lib.load()
+    check(lib.ns_merge_device(int(device), int(Q), int(k), int(nlists), C.c_void_p(d_hits), C.c_void_p(d_nhits),
+                              C.c_void_p(d_found), C.c_void_p(d_out_hits), C.c_void_p(d_out_nhits),
+                              C.c_void_p(d_out_found), C.c_void_p(stream) if stream else None))
+
+
+def query_terms(query: str) -> List[str]:
+    """tokenize + len<2/stopword filter (include/textutil.hpp:13-37, src/api_engine.cpp:391-397)."""
+    lib = _lib.load()
+    cap = 2 * len(query.encode("utf-8")) + 16
+    buf = C.create_string_buffer(cap)
+    n = lib.ns_text_query_terms(query.encode("utf-8"), buf, cap)
+    if n < 0:
+        raise RuntimeError("ns_text_query_terms: buffer too small")
+    raw = buf.raw
+    out, at = [], 0
+    for _ in range(n):
+        end = raw.index(b"\0", at)
+        out.append(raw[at:end].decode("ascii"))
+        at = end + 1
+    return out
+
+
+class Engine:
+    """Host mirror of cord19::Engine for the search path.
+
+    device=None builds a host-only engine (lexicon, tokenizer, resolve); its search() raises.
+    rank/world select this engine's segment shard (segment i -> rank i % world).
+    """
+
+    def __init__(self, index_dir: str, device: Optional[int] = 0, rank: int = 0, world: int = 1):
+        self._lib = _lib.load()
+        h = C.c_void_p()
+        check(self._lib.ns_engine_create(str(index_dir).encode(), -1 if device is None else int(device), C.byref(h)))
+        self._h = h
+        self.index_dir = str(index_dir)
+        self.device = device
+        self.rank, self.world = rank, world
+        check(self._lib.ns_engine_set_shard(self._h, rank, world))
+
+    # -- Engine::reload ------------------------------------------------------------------------
+    def reload(self) -> bool:
+        rc = self._lib.ns_engine_reload(self._h)
+        if rc == _lib.NS_OK:
+            return True
+        if rc == 3:  # NS_ERR_IO: the reference's `return false`
+            return False
+        check(rc)
+        return False
+
+    @property
+    def last_error(self) -> str:
+        return (self._lib.ns_last_error() or b"").decode("utf-8", "replace")
+
+    @property
+    def num_segments(self) -> int:
+        return int(self._lib.ns_engine_num_segments(self._h))
+
+    def segment_name(self, i: int) -> str:
+        buf = C.create_string_buffer(512)
+        n = self._lib.ns_engine_segment_name(self._h, i, buf, 512)
+        if n < 0:
+            raise IndexError(i)
+        return buf.value.decode()
+
+    @property
+    def seg_names(self) -> List[str]:
+        return [self.segment_name(i) for i in range(self.num_segments)]
+
+    def owns(self, seg: int) -> bool:
+        return seg % self.world == self.rank
+
+    def segment_stats(self, i: int) -> dict:
+        N, T, P, avg = C.c_uint32(), C.c_uint32(), C.c_uint64(), C.c_float()
+        check(self._lib.ns_engine_segment_stats(self._h, i, C.byref(N), C.byref(avg), C.byref(T), C.byref(P)))
+        return {"N": N.value, "avgdl": avg.value, "T": T.value, "P": P.value}
+
+    def term_stats(self, i: int, term: str) -> Tuple[int, int]:
+        df, cnt = C.c_uint32(), C.c_uint32()
+        check(self._lib.ns_engine_term_stats(self._h, i, term.encode(), C.byref(df), C.byref(cnt)))
+        return df.value, cnt.value
+
+    def cord_uid(self, seg: int, doc: int) -> str:
+        buf = C.create_string_buffer(4096)
+        n = self._lib.ns_engine_cord_uid(self._h, int(seg), int(doc), buf, 4096)
+        return buf.value.decode("utf-8", "replace") if n >= 0 else ""
+
+    @property
+    def index(self) -> DeviceIndex:
+        h = self._lib.ns_engine_index(self._h)
+        if not h:
+            raise RuntimeError("engine has no device index (created with device=None)")
+        return DeviceIndex(self.device, _borrowed=h, _owner=self)
+
+    # -- Engine::search ------------------------------------------------------------------------
+    def search(self, query: str, k: int = 10) -> dict:
+        q = query.encode("utf-8")
+        cap = 1 << 16
+        while True:
+            buf = C.create_string_buffer(cap)
+            need = C.c_size_t()
+            check(self._lib.ns_engine_search_json(self._h, q, int(k), buf, cap, C.byref(need)))
+            if need.value < cap:
+                return json.loads(buf.value.decode("utf-8"))
+            cap = need.value + 1
+
+    def resolve_batch(self, queries: Sequence[str]) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        """Host front end only: (q_off[Q+1] u64, terms QTERM_DTYPE, has_terms[Q] bool)."""
+        Q = len(queries)
+        arr = _cstr_array(queries)
+        q_off = np.zeros(Q + 1, dtype=np.uint64)
+        has = np.zeros(max(1, Q), dtype=np.uint8)
+        n = C.c_uint64()
+        check(self._lib.ns_engine_resolve_batch(self._h, Q, arr, _ptr(q_off), None, 0, C.byref(n), _ptr(has)))
+        terms = np.zeros(max(1, n.value), dtype=QTERM_DTYPE)
+        check(self._lib.ns_engine_resolve_batch(self._h, Q, arr, _ptr(q_off), _ptr(terms), len(terms), C.byref(n),
+                                                _ptr(has)))
+        return q_off, terms[: n.value], has[:Q].astype(bool)
+
+    def search_batch(self, queries: Sequence[str], k: int = 10) -> BatchResult:
+        """Q query strings through tokenizer, lexicon, H2D, kernels, D2H — the e2e call."""
+        Q = len(queries)
+        K = clamp_k(k)
+        arr = _cstr_array(queries)
+        hits = np.zeros((Q, K), dtype=HIT_DTYPE)
+        nhits = np.zeros(Q, dtype=np.uint32)
+        found = np.zeros(Q, dtype=np.uint64)
+        has = np.zeros(max(1, Q), dtype=np.uint8)
+        check(self._lib.ns_engine_search_batch(self._h, Q, arr, int(k), _ptr(hits), _ptr(nhits), _ptr(found), _ptr(has)))
+        return BatchResult(hits, nhits, found, has[:Q].astype(bool), K)
+
+    def close(self) -> None:
+        if self._h:
+            self._lib.ns_engine_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
