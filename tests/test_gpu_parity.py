@@ -1,0 +1,183 @@
+"""CUDA path vs oracle through the C ABI: bit-exact docIds, order, found and f32 score bits.
+
+Tolerance: none — scores are compared as u32 bit patterns (north_star allows 1e-5 relative; the
+kernels reproduce the reference's operation tree exactly, so the stricter bar holds).
+"""
+import os
+
+import numpy as np
+import pytest
+
+import nsb200
+from conftest import EDGE_QUERIES, assert_same_as_oracle, make_case
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def small_engine(small_case):
+    e = nsb200.Engine(small_case.path, device=0)
+    assert e.reload(), e.last_error
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def config1_engine(config1_case):
+    e = nsb200.Engine(config1_case.path, device=0)
+    assert e.reload(), e.last_error
+    yield e
+    e.close()
+
+
+@pytest.mark.parametrize("k", [1, 3, 10, 100])
+def test_small_two_segments(small_case, small_engine, k):
+    qs = nsb200.make_queries(small_case.spec, 300, 1, 5) + EDGE_QUERIES
+    assert_same_as_oracle(small_engine.search_batch(qs, k), small_case.oracle, qs, k)
+
+
+def test_k_is_clamped_like_the_reference(small_case, small_engine):
+    qs = nsb200.make_queries(small_case.spec, 20, 1, 3)
+    for k in (0, -5, 1000):
+        res = small_engine.search_batch(qs, k)
+        assert res.k == max(1, min(k, 100))
+        assert_same_as_oracle(res, small_case.oracle, qs, k)
+
+
+def test_config1_10k_docs(config1_case, config1_engine):
+    """BASELINE configs[0]: 1000 queries of 1-3 terms, query seed 7, k=10."""
+    qs = nsb200.make_queries(config1_case.spec, 1000, 1, 3, seed=nsb200.QUERY_SEED)
+    assert_same_as_oracle(config1_engine.search_batch(qs, 10), config1_case.oracle, qs, 10)
+
+
+def test_single_query_json_fields(small_case, small_engine):
+    for q in ["t1 t2", "T7, the t9!", "zzzz", "the of"]:
+        got = small_engine.search(q, 10)
+        want = small_case.oracle.search(q, 10)
+        assert got["k"] == want["k"] and got["segments"] == want["segments"] and got["query"] == q
+        assert got.get("found") == want["found"]
+        assert ("found" in got) == (want["found"] is not None)
+        assert [(r["segment"], r["docId"], r["cord_uid"]) for r in got["results"]] == \
+               [(r["segment"], r["docId"], r["cord_uid"]) for r in want["results"]]
+        # JSON carries the f32 widened to double: must round-trip to the same f32
+        assert [np.float32(r["score"]).view(np.uint32) for r in got["results"]] == \
+               [r["score_bits"] for r in want["results"]]
+
+
+@pytest.mark.parametrize("splits", [1, 2, 3, 7, 64])
+def test_splits_do_not_change_results(small_case, small_engine, splits):
+    """(query, split) decomposition + merge kernel == one CTA per query."""
+    qs = nsb200.make_queries(small_case.spec, 64, 1, 5) + EDGE_QUERIES
+    q_off, terms, has = small_engine.resolve_batch(qs)
+    idx = small_engine.index
+    for k in (10, 100):
+        b = idx.prepare(q_off, terms, k)
+        b.set_splits(splits)
+        b.launch()
+        hits, nhits, found = b.fetch()
+        b.close()
+        res = nsb200.BatchResult(hits, nhits, found, has, nsb200.clamp_k(k))
+        assert_same_as_oracle(res, small_case.oracle, qs, k)
+
+
+def test_single_query_batches(small_case, small_engine):
+    """Q=1 goes through the split path (many CTAs per query)."""
+    for q in nsb200.make_queries(small_case.spec, 12, 1, 5, seed=99):
+        assert_same_as_oracle(small_engine.search_batch([q], 10), small_case.oracle, [q], 10)
+
+
+def test_weighted_terms_via_abi(small_case, small_engine):
+    """Weights flow through ns_qterm.weight (semantic expansion, src/api_engine.cpp:410-421):
+    weight 2.0 on a single-term query must double every score exactly (power of two)."""
+    qs = ["t2", "t9", "t30"]
+    q_off, terms, _ = small_engine.resolve_batch(qs)
+    idx = small_engine.index
+    h1, n1, f1 = idx.search_batch(q_off, terms, 10)
+    t2 = terms.copy()
+    t2["weight"] = 2.0
+    h2, n2, f2 = idx.search_batch(q_off, t2, 10)
+    assert np.array_equal(n1, n2) and np.array_equal(f1, f2)
+    for q in range(len(qs)):
+        n = int(n1[q])
+        assert np.array_equal(h2["score"][q, :n], h1["score"][q, :n] * np.float32(2.0))
+        assert np.array_equal(h2["doc"][q, :n], h1["doc"][q, :n])
+
+
+def test_rejects_unsorted_postings():
+    idx = nsb200.DeviceIndex(0)
+    doc_len = np.full(16, 10, np.uint32)
+    post = np.array([[3, 1], [2, 1], [5, 1]], np.uint32)  # 3,2 out of order
+    with pytest.raises(nsb200._lib.NsError) as ei:
+        idx.add_segment(0, 10.0, doc_len, np.array([0], np.uint64), np.array([3], np.uint32), post)
+    assert ei.value.status == 4  # NS_ERR_FORMAT
+    post = np.array([[3, 1], [99, 1]], np.uint32)  # docId >= N
+    with pytest.raises(nsb200._lib.NsError):
+        idx.add_segment(0, 10.0, doc_len, np.array([0], np.uint64), np.array([2], np.uint32), post)
+    idx.close()
+
+
+def test_search_before_commit_fails_loudly():
+    idx = nsb200.DeviceIndex(0)
+    with pytest.raises(nsb200._lib.NsError) as ei:
+        idx.search_batch(np.zeros(2, np.uint64), np.zeros(0, nsb200.QTERM_DTYPE), 10)
+    assert ei.value.status == 6  # NS_ERR_STATE
+    idx.close()
+
+
+def test_reload_swaps_index_and_keeps_old_on_failure(workdir, small_case):
+    """Engine::reload semantics (src/api_engine.cpp:82-90): failure keeps the previous segments."""
+    import shutil
+    path = os.path.join(workdir, "reload_case")
+    shutil.copytree(small_case.path, path)
+    e = nsb200.Engine(path, device=0)
+    assert e.reload()
+    qs = nsb200.make_queries(small_case.spec, 32, 1, 3)
+    assert_same_as_oracle(e.search_batch(qs, 10), small_case.oracle, qs, 10)
+    os.remove(os.path.join(path, "segments", "seg_000002", "lexicon_b017.bin"))
+    assert e.reload() is False
+    assert_same_as_oracle(e.search_batch(qs, 10), small_case.oracle, qs, 10)
+    e.close()
+
+
+def test_tile_boundaries_and_ragged_segments(workdir):
+    """Segments whose sizes straddle the 8192-doc tile: 8191, 8192, 8193 docs and a 1-doc segment."""
+    spec = nsb200.CorpusSpec(vocab=800)
+    path = os.path.join(workdir, "ragged")
+    names = []
+    base = 0
+    for i, n in enumerate([8191, 8192, 8193, 1, 20000]):
+        name = nsb200.seg_name(i + 1)
+        nsb200.write_segment(spec, base, n, os.path.join(path, "segments", name))
+        names.append(name)
+        base += n
+    nsb200.write_manifest(path, names)
+    from oracle import oracle as orc
+    oi = orc.OracleIndex(path)
+    e = nsb200.Engine(path, device=0)
+    assert e.reload(), e.last_error
+    qs = nsb200.make_queries(spec, 200, 1, 5) + EDGE_QUERIES
+    for k in (10, 100):
+        assert_same_as_oracle(e.search_batch(qs, k), oi, qs, k)
+    e.close()
+
+
+def test_concurrent_callers(small_case, small_engine):
+    """ns_search_batch is callable from many host threads (the reference serialises on Engine::mtx)."""
+    import threading
+    qs = nsb200.make_queries(small_case.spec, 64, 1, 4)
+    _, s, g, d, nh, fo, hf = small_case.oracle.search_many(qs, 10, nthreads=4)
+    errs = []
+
+    def worker():
+        try:
+            for _ in range(5):
+                r = small_engine.search_batch(qs, 10)
+                assert np.array_equal(r.found, fo) and np.array_equal(r.nhits, nh)
+                assert np.array_equal(r.hits["doc"][0, : nh[0]], d[0, : nh[0]])
+        except Exception as ex:  # noqa: BLE001
+            errs.append(ex)
+
+    th = [threading.Thread(target=worker) for _ in range(8)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs
