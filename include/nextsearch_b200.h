@@ -146,6 +146,14 @@ int ns_merge_device(int device, uint32_t Q, int k, uint32_t nlists, const void* 
                     const void* d_nhits, const void* d_found, void* d_out_hits, void* d_out_nhits,
                     void* d_out_found, void* stream);
 
+/* The batch's whole result as one contiguous device blob (hits | nhits | found at the returned
+ * byte offsets): the unit ranks exchange with ONE all-gather per batch. */
+int ns_batch_result_blob(ns_batch* b, void** d_blob, uint64_t* bytes, uint64_t* off_nhits, uint64_t* off_found);
+/* Merge `nlists` such blobs laid out blob_stride bytes apart (the all-gather output). */
+int ns_merge_blobs_device(int device, uint32_t Q, int k, uint32_t nlists, const void* d_blobs,
+                          uint64_t blob_stride, uint64_t off_nhits, uint64_t off_found, void* d_out_hits,
+                          void* d_out_nhits, void* d_out_found, void* stream);
+
 /* ------------------------------------------------------------------ */
 /* Engine mirror (host).  Same surface as cord19::Engine for this path.*/
 /* ------------------------------------------------------------------ */

@@ -541,12 +541,13 @@ extern "C" int ns_batch_launch(ns_batch* b, void* stream) {
         NS_CUDA(cudaEventRecord(b->res->ev[1], s));
         if (b->S > 1) {
             MergeArgs m;
-            m.hits = a.hits;
-            m.nhits = a.nhits;
-            m.found = a.found;
-            m.ls = b->k;
+            m.hits = reinterpret_cast<const unsigned char*>(a.hits);
+            m.nhits = reinterpret_cast<const unsigned char*>(a.nhits);
+            m.found = reinterpret_cast<const unsigned char*>(a.found);
+            m.hits_lsb = (uint64_t)b->k * sizeof(ns_hit);
+            m.n_lsb = 4;
+            m.f_lsb = 8;
             m.qs = (uint64_t)b->S * b->k;
-            m.ls2 = 1;
             m.qs2 = b->S;
             m.Q = b->Q;
             m.k = b->k;
@@ -630,24 +631,25 @@ extern "C" int ns_search_batch(ns_index* idx, uint32_t Q, int k, const uint64_t*
     return rc;
 }
 
-extern "C" int ns_merge_device(int device, uint32_t Q, int k_in, uint32_t nlists, const void* d_hits,
-                               const void* d_nhits, const void* d_found, void* d_out_hits, void* d_out_nhits,
-                               void* d_out_found, void* stream) {
+static int merge_launch(int device, uint32_t Q, int k_in, uint32_t nlists, const void* d_hits, const void* d_nhits,
+                        const void* d_found, uint64_t hits_lsb, uint64_t n_lsb, uint64_t f_lsb, void* d_out_hits,
+                        void* d_out_nhits, void* d_out_found, void* stream) {
     if (!d_hits || !d_nhits || !d_found || !d_out_hits || !d_out_nhits || !d_out_found) {
-        set_error("ns_merge_device: null argument");
+        set_error("ns_merge: null argument");
         return NS_ERR_INVALID;
     }
-    if (nlists == 0 || nlists > (uint32_t)kMergeMaxLists) { set_error("ns_merge_device: nlists out of range"); return NS_ERR_INVALID; }
+    if (nlists == 0 || nlists > (uint32_t)kMergeMaxLists) { set_error("ns_merge: nlists out of range"); return NS_ERR_INVALID; }
     NS_CUDA(cudaSetDevice(device));
     const uint32_t k = (uint32_t)std::max(1, std::min(k_in, NS_MAX_K));
     if (Q == 0) return NS_OK;
     MergeArgs m;
-    m.hits = static_cast<const ns_hit*>(d_hits);
-    m.nhits = static_cast<const uint32_t*>(d_nhits);
-    m.found = static_cast<const unsigned long long*>(d_found);
-    m.ls = (uint64_t)Q * k;
+    m.hits = static_cast<const unsigned char*>(d_hits);
+    m.nhits = static_cast<const unsigned char*>(d_nhits);
+    m.found = static_cast<const unsigned char*>(d_found);
+    m.hits_lsb = hits_lsb;
+    m.n_lsb = n_lsb;
+    m.f_lsb = f_lsb;
     m.qs = k;
-    m.ls2 = Q;
     m.qs2 = 1;
     m.Q = Q;
     m.k = k;
@@ -659,4 +661,30 @@ extern "C" int ns_merge_device(int device, uint32_t Q, int k_in, uint32_t nlists
     topk_merge_kernel<<<(Q + kMergeWarps - 1) / kMergeWarps, kMergeWarps * 32, smem, (cudaStream_t)stream>>>(m);
     NS_CUDA(cudaGetLastError());
     return NS_OK;
+}
+
+extern "C" int ns_merge_device(int device, uint32_t Q, int k_in, uint32_t nlists, const void* d_hits,
+                               const void* d_nhits, const void* d_found, void* d_out_hits, void* d_out_nhits,
+                               void* d_out_found, void* stream) {
+    const uint32_t k = (uint32_t)std::max(1, std::min(k_in, NS_MAX_K));
+    return merge_launch(device, Q, k_in, nlists, d_hits, d_nhits, d_found, (uint64_t)Q * k * sizeof(ns_hit),
+                        (uint64_t)Q * 4, (uint64_t)Q * 8, d_out_hits, d_out_nhits, d_out_found, stream);
+}
+
+extern "C" int ns_batch_result_blob(ns_batch* b, void** d_blob, uint64_t* bytes, uint64_t* off_nhits, uint64_t* off_found) {
+    if (!b) return NS_ERR_INVALID;
+    if (d_blob) *d_blob = b->d_out;
+    if (bytes) *bytes = b->out_bytes;
+    if (off_nhits) *off_nhits = b->off_n;
+    if (off_found) *off_found = b->off_found;
+    return NS_OK;
+}
+
+extern "C" int ns_merge_blobs_device(int device, uint32_t Q, int k, uint32_t nlists, const void* d_blobs,
+                                     uint64_t blob_stride, uint64_t off_nhits, uint64_t off_found, void* d_out_hits,
+                                     void* d_out_nhits, void* d_out_found, void* stream) {
+    if (!d_blobs) { set_error("ns_merge_blobs_device: null argument"); return NS_ERR_INVALID; }
+    const unsigned char* base = static_cast<const unsigned char*>(d_blobs);
+    return merge_launch(device, Q, k, nlists, base, base + off_nhits, base + off_found, blob_stride, blob_stride,
+                        blob_stride, d_out_hits, d_out_nhits, d_out_found, stream);
 }

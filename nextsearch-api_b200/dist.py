@@ -1,0 +1,141 @@
+"""Segment-sharded search over the GPUs of one box.
+
+One process per GPU (torch.distributed, NCCL).  Segment i lives on rank i % world; every rank
+receives the same query batch, scores its own segments, and the per-rank result blobs
+(hits | nhits | found) are exchanged with ONE all-gather per batch and merged on every rank by
+ns_merge_blobs_device under the total order (score desc, segment asc, docId asc).  Scores are
+segment-local in the reference (src/api_engine.cpp:461,478), so no other exchange exists.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import check
+from .engine import HIT_DTYPE, Batch, BatchResult, Engine, clamp_k
+
+import ctypes as C
+
+_ALIGN = 256
+
+
+def _up(n: int) -> int:
+    return (n + _ALIGN - 1) // _ALIGN * _ALIGN
+
+
+def blob_layout(Q: int, k: int) -> Tuple[int, int, int]:
+    """(bytes, off_nhits, off_found) of one rank's result blob — mirrors ns_batch_prepare."""
+    k = clamp_k(k)
+    sz_hits = _up(max(1, Q * k) * HIT_DTYPE.itemsize)
+    sz_n = _up(max(1, Q) * 4)
+    sz_f = _up(max(1, Q) * 8)
+    return sz_hits + sz_n + sz_f, sz_hits, sz_hits + sz_n
+
+
+def pack_blob(hits: np.ndarray, nhits: np.ndarray, found: np.ndarray, k: int) -> np.ndarray:
+    Q = len(nhits)
+    total, off_n, off_f = blob_layout(Q, k)
+    blob = np.zeros(total, np.uint8)
+    blob[: Q * clamp_k(k) * HIT_DTYPE.itemsize] = np.ascontiguousarray(hits, HIT_DTYPE).view(np.uint8).reshape(-1)
+    blob[off_n: off_n + Q * 4] = np.ascontiguousarray(nhits, np.uint32).view(np.uint8)
+    blob[off_f: off_f + Q * 8] = np.ascontiguousarray(found, np.uint64).view(np.uint8)
+    return blob
+
+
+def unpack_blob(blob: np.ndarray, Q: int, k: int):
+    k = clamp_k(k)
+    _, off_n, off_f = blob_layout(Q, k)
+    hits = blob[: Q * k * HIT_DTYPE.itemsize].view(HIT_DTYPE).reshape(Q, k)
+    nhits = blob[off_n: off_n + Q * 4].view(np.uint32)
+    found = blob[off_f: off_f + Q * 8].view(np.uint64)
+    return hits, nhits, found
+
+
+def owner_of_segment(seg: int, world: int) -> int:
+    return seg % world
+
+
+class _DevMem:
+    """Expose raw device memory to torch through __cuda_array_interface__ (no copy)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+@dataclass
+class ShardedBatch:
+    batch: Batch
+    has_found: np.ndarray
+    Q: int
+    k: int
+    local_blob: "object"      # torch uint8 view of the batch's device result blob
+    gathered: "object"        # torch uint8 [world * blob_bytes]
+    out_hits: "object"        # torch uint8 [Q*k*12]
+    out_nhits: "object"       # torch int32 [Q]
+    out_found: "object"       # torch int64 [Q]
+    blob_bytes: int
+    off_n: int
+    off_f: int
+
+
+class ShardedSearcher:
+    def __init__(self, index_dir: str, device: int, rank: int, world: int, group=None):
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist = torch, dist
+        self.rank, self.world, self.device, self.group = rank, world, device, group
+        self.engine = Engine(index_dir, device=device, rank=rank, world=world)
+
+    def reload(self) -> bool:
+        return self.engine.reload()
+
+    def prepare(self, queries: Sequence[str], k: int) -> ShardedBatch:
+        torch = self.torch
+        q_off, terms, has = self.engine.resolve_batch(queries)
+        b = self.engine.index.prepare(q_off, terms, k)
+        lib = _lib.load()
+        ptr, nbytes, off_n, off_f = C.c_void_p(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+        check(lib.ns_batch_result_blob(b._h, C.byref(ptr), C.byref(nbytes), C.byref(off_n), C.byref(off_f)))
+        dev = torch.device("cuda", self.device)
+        local = torch.as_tensor(_DevMem(ptr.value, nbytes.value), device=dev)
+        Q, K = len(queries), clamp_k(k)
+        return ShardedBatch(
+            batch=b, has_found=has, Q=Q, k=K, local_blob=local,
+            gathered=torch.empty(self.world * nbytes.value, dtype=torch.uint8, device=dev),
+            out_hits=torch.empty(max(1, Q * K) * HIT_DTYPE.itemsize, dtype=torch.uint8, device=dev),
+            out_nhits=torch.empty(max(1, Q), dtype=torch.int32, device=dev),
+            out_found=torch.empty(max(1, Q), dtype=torch.int64, device=dev),
+            blob_bytes=nbytes.value, off_n=off_n.value, off_f=off_f.value)
+
+    def launch(self, sb: ShardedBatch) -> None:
+        """score+top-k on this rank's segments -> all-gather -> merge, all on torch's current stream."""
+        torch, dist = self.torch, self.dist
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        sb.batch.launch(stream)
+        if self.world > 1:
+            dist.all_gather_into_tensor(sb.gathered, sb.local_blob, group=self.group)
+            src = sb.gathered
+        else:
+            src = sb.local_blob
+        lib = _lib.load()
+        check(lib.ns_merge_blobs_device(self.device, sb.Q, sb.k, self.world, C.c_void_p(src.data_ptr()),
+                                        sb.blob_bytes, sb.off_n, sb.off_f, C.c_void_p(sb.out_hits.data_ptr()),
+                                        C.c_void_p(sb.out_nhits.data_ptr()), C.c_void_p(sb.out_found.data_ptr()),
+                                        C.c_void_p(stream) if stream else None))
+
+    def fetch(self, sb: ShardedBatch) -> BatchResult:
+        hits = sb.out_hits.cpu().numpy()[: sb.Q * sb.k * HIT_DTYPE.itemsize].view(HIT_DTYPE).reshape(sb.Q, sb.k)
+        nhits = sb.out_nhits.cpu().numpy()[: sb.Q].view(np.uint32)
+        found = sb.out_found.cpu().numpy()[: sb.Q].view(np.uint64)
+        return BatchResult(hits, nhits, found, sb.has_found, sb.k)
+
+    def search_batch(self, queries: Sequence[str], k: int = 10) -> BatchResult:
+        sb = self.prepare(queries, k)
+        self.launch(sb)
+        res = self.fetch(sb)
+        sb.batch.close()
+        return res

@@ -12,12 +12,13 @@
 //        feed a corpus dump (written by ns_corpus_write_segment(dump_path=…)) through
 //        SegmentWriter::add_document / write_segment (include/segment_writer.hpp:48-168)
 //   ref_engine manifest <index_dir> <seg>...          save_manifest (src/api_segment.cpp:29-35)
-//   ref_engine search <index_dir> <queries.txt> <k> <out.jsonl|-> [first] [count]
+//   ref_engine search <index_dir> <queries.txt> <k> <out.jsonl|-> [first] [count] [latencies.txt]
 //        Engine::reload() + Engine::search(line, k) per line, run from a fresh empty CWD so that no
 //        stale search_cache.json is served (src/api_engine.cpp:156,380-385); one JSON object per
 //        query is written to out.jsonl ("-" = none), a timing summary to stdout.
 #include <unistd.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstring>
@@ -71,6 +72,7 @@ static int mode_search(int argc, char** argv) {
     std::string out = std::strcmp(argv[5], "-") == 0 ? std::string() : fs::absolute(argv[5]).string();
     long first = argc > 6 ? std::atol(argv[6]) : 0;
     long count = argc > 7 ? std::atol(argv[7]) : -1;
+    std::string latfile = argc > 8 ? fs::absolute(argv[8]).string() : std::string();
 
     std::vector<std::string> queries;
     {
@@ -120,6 +122,11 @@ static int mode_search(int argc, char** argv) {
                 }
             }
         }
+        if (!latfile.empty()) {
+            std::ofstream lf(latfile);
+            lf.precision(9);
+            for (double v : lat) lf << v << "\n";
+        }
         std::sort(lat.begin(), lat.end());
         json s;
         s["queries"] = queries.size();
@@ -148,6 +155,6 @@ int main(int argc, char** argv) {
     }
     if (argc >= 6 && std::strcmp(argv[1], "search") == 0) return mode_search(argc, argv);
     std::cerr << "usage: ref_engine write <dump> <segdir> | manifest <index_dir> <seg>... | "
-                 "search <index_dir> <queries.txt> <k> <out.jsonl|-> [first] [count]\n";
+                 "search <index_dir> <queries.txt> <k> <out.jsonl|-> [first] [count] [latencies.txt]\n";
     return 64;
 }
