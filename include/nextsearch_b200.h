@@ -236,6 +236,10 @@ int ns_corpus_make_queries(const ns_corpus_spec* spec, uint64_t query_seed, uint
                            uint32_t min_terms, uint32_t max_terms, uint32_t head_ranks,
                            char* buf, size_t cap, size_t* needed);
 
+/* Device self-test: compares the kernels' inline correctly-rounded division with div.rn.f32 on n
+ * pseudo-random operand pairs drawn from the validated range; *mismatches must come back 0. */
+int ns_selftest_fastdiv(int device, uint64_t n, uint64_t seed, uint64_t* mismatches);
+
 #ifdef __cplusplus
 }
 #endif

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
@@ -41,23 +43,28 @@ struct SegState {
     uint64_t P = 0;
     float avgdl = 0.f;
     uint2* d_post = nullptr;
-    float* d_norm = nullptr;
+    float* d_norm = nullptr;   // per doc (unpacked segments)
+    float* d_lut = nullptr;    // per distinct doc length (packed segments)
+    bool packed = false;
     uint32_t* d_tileoff = nullptr;
     std::vector<uint32_t> h_count;  // LexEntry.count per row (query weights, row validation)
     uint64_t bytes = 0;
+    bool norm_in_range = true;      // every norm[] value validated for div_rn_inrange
     void release() {
         if (d_post) cudaFree(d_post);
         if (d_norm) cudaFree(d_norm);
+        if (d_lut) cudaFree(d_lut);
         if (d_tileoff) cudaFree(d_tileoff);
         d_post = nullptr;
         d_norm = nullptr;
+        d_lut = nullptr;
         d_tileoff = nullptr;
     }
 };
 
 struct IndexState {
     int device = 0;
-    uint32_t tile_docs = 8192;
+    uint32_t tile_docs = 2048;
     std::vector<SegState> segs;  // ascending gseg
     std::unordered_map<uint32_t, uint32_t> slot_of;
     DevSeg* d_segs = nullptr;
@@ -98,7 +105,7 @@ struct BatchRes {
 
 struct ns_index {
     int device = 0;
-    uint32_t tile_docs = 8192;
+    uint32_t tile_docs = 2048;
     std::mutex mu;
     std::shared_ptr<IndexState> live;
     std::vector<SegState> staged;
@@ -110,21 +117,28 @@ struct ns_batch {
     ns_index* owner = nullptr;
     std::shared_ptr<IndexState> st;
     std::unique_ptr<BatchRes> res;
-    uint32_t Q = 0, k = 0, S = 1;
+    uint32_t Q = 0, k = 0;
+    uint32_t nitems = 0, max_split = 1;
+    bool scan_always = false;
+    bool fast = false;  // operand ranges validated + unit weights: FAST kernel variant
     uint64_t nterms = 0, postings = 0;
-    // device sub-arrays
+    std::vector<uint64_t> weight;  // postings per query (host copy, for re-splitting)
+    // device sub-arrays of the input blob
     uint32_t* d_qoff = nullptr;
     DevTerm* d_terms = nullptr;
-    uint32_t* d_order = nullptr;
+    DevItem* d_items = nullptr;
+    uint32_t* d_list_off = nullptr;
+    uint32_t* d_counter = nullptr;
+    size_t off_items = 0, off_list = 0, off_counter = 0, in_bytes = 0, items_cap = 0;
     uint8_t* d_out = nullptr;  // hits | nhits | found, contiguous == h_out layout
     ns_hit* d_out_hits = nullptr;
     uint32_t* d_out_n = nullptr;
     unsigned long long* d_out_found = nullptr;
     size_t out_bytes = 0, off_n = 0, off_found = 0;
-    // partial (split) results, allocated on demand
+    // per-item partial lists, allocated on demand
     uint8_t* d_part = nullptr;
     size_t d_part_cap = 0;
-    bool launched = false, has_merge = false;
+    bool launched = false;
 };
 
 extern "C" const char* ns_last_error(void) { return last_error(); }
@@ -154,7 +168,7 @@ extern "C" int ns_index_create(int device, ns_index** out) {
     idx->sm_count = prop.multiProcessorCount;
     if (const char* t = std::getenv("NSB200_TILE_DOCS")) {
         int v = std::atoi(t);
-        if (v == 4096 || v == 8192 || v == 16384) idx->tile_docs = (uint32_t)v;
+        if (v == 1024 || v == 2048 || v == 4096) idx->tile_docs = (uint32_t)v;
     }
     *out = idx;
     return NS_OK;
@@ -196,12 +210,27 @@ extern "C" int ns_index_add_segment(ns_index* idx, uint32_t global_seg, uint32_t
     if (s.ntiles == 0) s.ntiles = 1;
     s.h_count.assign(term_count, term_count + T);
 
+    // Distinct doc lengths -> 16-bit codes (packed payload).  Falls back to the per-doc norm array
+    // when the segment has more than 65536 distinct lengths or (checked on the device) a tf >= 65536.
+    std::vector<uint32_t> uniq(doc_len, doc_len + N);
+    std::sort(uniq.begin(), uniq.end());
+    uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+    bool can_pack = uniq.size() <= 65536 && !std::getenv("NSB200_NO_PACK");
+    std::vector<unsigned short> code;
+    if (can_pack) {
+        code.resize(N);
+        for (uint32_t d = 0; d < N; d++)
+            code[d] = (unsigned short)(std::lower_bound(uniq.begin(), uniq.end(), doc_len[d]) - uniq.begin());
+    }
+
     uint32_t *d_len = nullptr, *d_begin = nullptr, *d_count = nullptr;
-    unsigned int* d_err = nullptr;
+    unsigned short* d_code = nullptr;
+    unsigned int* d_err = nullptr;  // [0] posting-order violations, [1] norms outside the fast-division range, [2] tf > 0xFFFF
     auto cleanup = [&]() {
         if (d_len) cudaFree(d_len);
         if (d_begin) cudaFree(d_begin);
         if (d_count) cudaFree(d_count);
+        if (d_code) cudaFree(d_code);
         if (d_err) cudaFree(d_err);
     };
 #define NS_CUDA_SEG(expr)                                                                       \
@@ -216,25 +245,18 @@ extern "C" int ns_index_add_segment(ns_index* idx, uint32_t global_seg, uint32_t
     } while (0)
 
     const size_t tile_entries = (size_t)T * (s.ntiles + 1);
+    const size_t nlen = can_pack ? uniq.size() : (size_t)N;  // lengths the norm kernel evaluates
     NS_CUDA_SEG(cudaMalloc(&s.d_post, std::max<size_t>(16, P * sizeof(uint2))));
-    NS_CUDA_SEG(cudaMalloc(&s.d_norm, std::max<size_t>(16, (size_t)N * sizeof(float))));
     NS_CUDA_SEG(cudaMalloc(&s.d_tileoff, std::max<size_t>(16, tile_entries * sizeof(uint32_t))));
-    NS_CUDA_SEG(cudaMalloc(&d_len, std::max<size_t>(16, (size_t)N * 4)));
+    NS_CUDA_SEG(cudaMalloc(&d_len, std::max<size_t>(16, nlen * 4)));
     NS_CUDA_SEG(cudaMalloc(&d_begin, std::max<size_t>(16, (size_t)T * 4)));
     NS_CUDA_SEG(cudaMalloc(&d_count, std::max<size_t>(16, (size_t)T * 4)));
-    NS_CUDA_SEG(cudaMalloc(&d_err, sizeof(unsigned int)));
-    NS_CUDA_SEG(cudaMemset(d_err, 0, sizeof(unsigned int)));
+    NS_CUDA_SEG(cudaMalloc(&d_err, 3 * sizeof(unsigned int)));
+    NS_CUDA_SEG(cudaMemset(d_err, 0, 3 * sizeof(unsigned int)));
     if (P) NS_CUDA_SEG(cudaMemcpy(s.d_post, postings, P * sizeof(uint2), cudaMemcpyHostToDevice));
-    if (N) NS_CUDA_SEG(cudaMemcpy(d_len, doc_len, (size_t)N * 4, cudaMemcpyHostToDevice));
     if (T) {
         NS_CUDA_SEG(cudaMemcpy(d_begin, begin32.data(), (size_t)T * 4, cudaMemcpyHostToDevice));
         NS_CUDA_SEG(cudaMemcpy(d_count, term_count, (size_t)T * 4, cudaMemcpyHostToDevice));
-    }
-    if (N) {
-        doc_norm_kernel<<<(N + 255) / 256, 256>>>(d_len, s.d_norm, N, avgdl, kK1, kB);
-        NS_CUDA_SEG(cudaGetLastError());
-    }
-    if (T) {
         const int blocks = (int)std::min<uint64_t>(((uint64_t)T + 7) / 8, (uint64_t)idx->sm_count * 32);
         validate_rows_kernel<<<blocks, 256>>>(s.d_post, d_begin, d_count, T, N, d_err);
         NS_CUDA_SEG(cudaGetLastError());
@@ -243,9 +265,40 @@ extern "C" int ns_index_add_segment(ns_index* idx, uint32_t global_seg, uint32_t
             s.d_post, d_begin, d_count, T, s.ntiles, idx->tile_docs, s.d_tileoff);
         NS_CUDA_SEG(cudaGetLastError());
     }
-    unsigned int h_err = 0;
-    NS_CUDA_SEG(cudaMemcpy(&h_err, d_err, sizeof(h_err), cudaMemcpyDeviceToHost));
+    unsigned int h_errs[3] = {0, 0, 0};
+    NS_CUDA_SEG(cudaMemcpy(h_errs, d_err, sizeof(h_errs), cudaMemcpyDeviceToHost));
+    if (h_errs[2]) can_pack = false;
+    float* d_normdst = nullptr;
+    if (can_pack) {
+        NS_CUDA_SEG(cudaMalloc(&s.d_lut, std::max<size_t>(16, uniq.size() * sizeof(float))));
+        if (!uniq.empty()) NS_CUDA_SEG(cudaMemcpy(d_len, uniq.data(), uniq.size() * 4, cudaMemcpyHostToDevice));
+        d_normdst = s.d_lut;
+    } else {
+        if (nlen < (size_t)N) {  // d_len was sized for the distinct lengths: regrow
+            cudaFree(d_len);
+            d_len = nullptr;
+            NS_CUDA_SEG(cudaMalloc(&d_len, std::max<size_t>(16, (size_t)N * 4)));
+        }
+        NS_CUDA_SEG(cudaMalloc(&s.d_norm, std::max<size_t>(16, (size_t)N * sizeof(float))));
+        if (N) NS_CUDA_SEG(cudaMemcpy(d_len, doc_len, (size_t)N * 4, cudaMemcpyHostToDevice));
+        d_normdst = s.d_norm;
+    }
+    const uint32_t nnorm = can_pack ? (uint32_t)uniq.size() : N;
+    if (nnorm) {
+        doc_norm_kernel<<<(nnorm + 255) / 256, 256>>>(d_len, d_normdst, nnorm, avgdl, kK1, kB, d_err + 1);
+        NS_CUDA_SEG(cudaGetLastError());
+    }
+    if (can_pack && P) {
+        NS_CUDA_SEG(cudaMalloc(&d_code, std::max<size_t>(16, (size_t)N * 2)));
+        NS_CUDA_SEG(cudaMemcpy(d_code, code.data(), (size_t)N * 2, cudaMemcpyHostToDevice));
+        pack_postings_kernel<<<idx->sm_count * 16, 256>>>(s.d_post, P, d_code);
+        NS_CUDA_SEG(cudaGetLastError());
+    }
+    s.packed = can_pack;
+    NS_CUDA_SEG(cudaMemcpy(h_errs, d_err, sizeof(h_errs), cudaMemcpyDeviceToHost));
     NS_CUDA_SEG(cudaDeviceSynchronize());
+    const unsigned int h_err = h_errs[0];
+    s.norm_in_range = (h_errs[1] == 0);
     cleanup();
 #undef NS_CUDA_SEG
     if (h_err) {
@@ -254,7 +307,7 @@ extern "C" int ns_index_add_segment(ns_index* idx, uint32_t global_seg, uint32_t
                   " postings are out of order, duplicated or have docId >= N");
         return NS_ERR_FORMAT;
     }
-    s.bytes = P * sizeof(uint2) + (uint64_t)N * 4 + tile_entries * 4;
+    s.bytes = P * sizeof(uint2) + (can_pack ? (uint64_t)uniq.size() * 4 : (uint64_t)N * 4) + tile_entries * 4;
     std::lock_guard<std::mutex> lk(idx->mu);
     for (auto& o : idx->staged) {
         if (o.gseg == global_seg) {
@@ -290,6 +343,9 @@ extern "C" int ns_index_commit(ns_index* idx) {
         DevSeg d;
         d.post = s.d_post;
         d.norm = s.d_norm;
+        d.lut = s.d_lut;
+        d.packed = s.packed ? 1u : 0u;
+        d.pad_ = 0;
         d.tileoff = s.d_tileoff;
         d.ndocs = s.ndocs;
         d.T = s.T;
@@ -363,29 +419,69 @@ int acquire_res(ns_index* idx, size_t d_need, size_t in_need, size_t out_need, s
     return NS_OK;
 }
 
-uint32_t auto_splits(const ns_index* idx, const IndexState& st, uint32_t Q) {
-    if (const char* s = std::getenv("NSB200_SPLITS")) {
-        int v = std::atoi(s);
-        if (v > 0) return std::min<uint32_t>((uint32_t)v, std::max<uint32_t>(1, st.total_tiles));
+constexpr uint32_t kMaxSplit = 64;
+
+// Cut queries into items of roughly `target` postings (at most kMaxSplit per query, never more
+// than the tile count), order items heaviest first, write items + list_off into the pinned input
+// blob.  forced > 0 gives every query exactly min(forced, tiles) items (tests).
+void build_items(ns_batch* b, uint32_t forced) {
+    const IndexState& st = *b->st;
+    const uint32_t Q = b->Q;
+    const uint32_t tiles = std::max<uint32_t>(1, st.total_tiles);
+    uint64_t target = 32768;
+    if (const char* s = std::getenv("NSB200_ITEM_POSTINGS")) {
+        long v = std::atol(s);
+        if (v > 0) target = (uint64_t)v;
     }
-    // enough CTAs for ~2 waves at 6 CTAs/SM
-    const uint32_t target = (uint32_t)idx->sm_count * 12;
-    if (Q >= target) return 1;
-    uint32_t s = (target + Q - 1) / std::max<uint32_t>(1, Q);
-    s = std::min<uint32_t>(s, std::max<uint32_t>(1, st.total_tiles));
-    s = std::min<uint32_t>(s, (uint32_t)kMergeMaxLists);
-    return std::max<uint32_t>(1, s);
+    // small batches: cut finer so that every resident warp has work
+    const uint64_t want_items = (uint64_t)b->owner->sm_count * 24 * 2;
+    if (Q > 0 && b->postings / target + Q < want_items) target = std::max<uint64_t>(1024, b->postings / want_items);
+    std::vector<uint32_t> nsplit(Q);
+    std::vector<uint32_t> list_off((size_t)Q + 1, 0);
+    uint32_t maxs = 1;
+    for (uint32_t q = 0; q < Q; q++) {
+        uint64_t ns = forced ? forced : (b->weight[q] + target - 1) / target;
+        ns = std::max<uint64_t>(1, std::min<uint64_t>(ns, std::min<uint64_t>(tiles, kMaxSplit)));
+        nsplit[q] = (uint32_t)ns;
+        maxs = std::max(maxs, nsplit[q]);
+        list_off[q + 1] = list_off[q] + nsplit[q];
+    }
+    const uint32_t nitems = list_off[Q];
+    std::vector<std::pair<uint64_t, DevItem>> items;
+    items.reserve(nitems);
+    for (uint32_t q = 0; q < Q; q++)
+        for (uint32_t sp = 0; sp < nsplit[q]; sp++)
+            items.push_back({b->weight[q] / nsplit[q], DevItem{q, (sp << 16) | nsplit[q]}});
+    std::stable_sort(items.begin(), items.end(), [](const auto& x, const auto& y) { return x.first > y.first; });
+    DevItem* h_items = reinterpret_cast<DevItem*>(b->res->h_in + b->off_items);
+    for (uint32_t i = 0; i < nitems; i++) h_items[i] = items[i].second;
+    std::memcpy(b->res->h_in + b->off_list, list_off.data(), ((size_t)Q + 1) * 4);
+    b->nitems = nitems;
+    b->max_split = maxs;
 }
 
-template <int TD>
-cudaError_t launch_score(const ScoreArgs& a, cudaStream_t s) {
-    const size_t smem = (size_t)TD * sizeof(float);
-    if (smem > 48 * 1024) {  // per device, cheap: set on every launch
-        cudaError_t e = cudaFuncSetAttribute(bm25_score_topk_kernel<TD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
+struct KernelCfg {
+    const void* fn;
+    size_t smem;
+};
+
+template <int TDW, int KCAP, bool FAST>
+KernelCfg cfg_of() {
+    return KernelCfg{(const void*)bm25_score_topk_kernel<TDW, KCAP, FAST>, sizeof(WarpSmem<TDW, KCAP>) * kWarpsPerBlock};
+}
+
+template <int TDW>
+KernelCfg pick_kernel_t(uint32_t k, bool fast) {
+    if (k <= 16) return fast ? cfg_of<TDW, 16, true>() : cfg_of<TDW, 16, false>();
+    return fast ? cfg_of<TDW, 104, true>() : cfg_of<TDW, 104, false>();
+}
+
+KernelCfg pick_kernel(uint32_t tile_docs, uint32_t k, bool fast) {
+    switch (tile_docs) {
+        case 1024: return pick_kernel_t<1024>(k, fast);
+        case 4096: return pick_kernel_t<4096>(k, fast);
+        default: return pick_kernel_t<2048>(k, fast);
     }
-    bm25_score_topk_kernel<TD><<<a.Q * a.S, kThreads, smem, s>>>(a);
-    return cudaGetLastError();
 }
 
 }  // namespace
@@ -408,8 +504,12 @@ extern "C" int ns_batch_prepare(ns_index* idx, uint32_t Q, int k_in, const uint6
     std::vector<DevTerm> kept;
     kept.reserve(nin);
     std::vector<uint32_t> qoff32((size_t)Q + 1, 0);
-    std::vector<uint64_t> weight(Q, 0);
+    auto b = std::make_unique<ns_batch>();
+    b->weight.assign(Q, 0);
     uint64_t total_post = 0;
+    bool scan_always = false;
+    bool fast = true;
+    for (auto& sg : st->segs) fast = fast && sg.norm_in_range;
     for (uint32_t q = 0; q < Q; q++) {
         if (q_off[q + 1] < q_off[q]) { set_error("ns_batch_prepare: q_off not monotone"); return NS_ERR_INVALID; }
         uint32_t prev_slot = 0, in_seg = 0;
@@ -428,30 +528,38 @@ extern "C" int ns_batch_prepare(ns_index* idx, uint32_t Q, int k_in, const uint6
             const uint32_t cnt = sg.h_count[t.row];
             if (cnt == 0) continue;
             if (++in_seg > NS_MAX_TERMS) { set_error("ns_batch_prepare: more than NS_MAX_TERMS terms for one (query, segment)"); return NS_ERR_INVALID; }
+            // negative or NaN contribution: partial sums are not monotone -> dense scan per tile
+            if (!(t.weight >= 0.0f) || !(t.idf >= 0.0f)) scan_always = true;
+            // FAST kernel: qweight == 1.0f and idf in [2^-40, 2^6] (see div_rn_inrange)
+            if (t.weight != 1.0f || !(t.idf >= 9.094947017729282e-13f && t.idf <= 64.0f)) fast = false;
             kept.push_back(DevTerm{slot, t.row, t.idf, t.weight});
-            weight[q] += cnt;
+            b->weight[q] += cnt;
         }
         if (kept.size() > 0xFFFFFFF0ull) { set_error("ns_batch_prepare: too many terms"); return NS_ERR_INVALID; }
         qoff32[q + 1] = (uint32_t)kept.size();
-        total_post += weight[q];
+        total_post += b->weight[q];
     }
-    std::vector<uint32_t> order(Q);
-    std::iota(order.begin(), order.end(), 0u);
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return weight[a] > weight[b]; });
 
-    auto b = std::make_unique<ns_batch>();
     b->owner = idx;
     b->st = st;
     b->Q = Q;
     b->k = k;
     b->nterms = kept.size();
     b->postings = total_post;
-    b->S = auto_splits(idx, *st, Q);
+    b->scan_always = scan_always;
+    b->fast = fast && !scan_always;
 
+    const size_t tiles = std::max<uint32_t>(1, st->total_tiles);
+    b->items_cap = (size_t)Q * std::min<size_t>(tiles, kMaxSplit);
     const size_t sz_qoff = align_up(((size_t)Q + 1) * 4);
     const size_t sz_terms = align_up(std::max<size_t>(1, kept.size()) * sizeof(DevTerm));
-    const size_t sz_order = align_up(std::max<size_t>(1, Q) * 4);
-    const size_t in_bytes = sz_qoff + sz_terms + sz_order;
+    const size_t sz_items = align_up(std::max<size_t>(1, b->items_cap) * sizeof(DevItem));
+    const size_t sz_list = align_up(((size_t)Q + 1) * 4);
+    const size_t sz_counter = align_up(4);
+    b->off_items = sz_qoff + sz_terms;
+    b->off_list = b->off_items + sz_items;
+    b->off_counter = b->off_list + sz_list;
+    b->in_bytes = b->off_counter + sz_counter;
     const size_t sz_hits = align_up(std::max<size_t>(1, (size_t)Q * k) * sizeof(ns_hit));
     const size_t sz_n = align_up(std::max<size_t>(1, Q) * 4);
     const size_t sz_found = align_up(std::max<size_t>(1, Q) * 8);
@@ -459,28 +567,31 @@ extern "C" int ns_batch_prepare(ns_index* idx, uint32_t Q, int k_in, const uint6
     b->off_n = sz_hits;
     b->off_found = sz_hits + sz_n;
 
-    int rc = acquire_res(idx, in_bytes + b->out_bytes, in_bytes, b->out_bytes, b->res);
+    int rc = acquire_res(idx, b->in_bytes + b->out_bytes, b->in_bytes, b->out_bytes, b->res);
     if (rc != NS_OK) return rc;
     BatchRes& r = *b->res;
     std::memcpy(r.h_in, qoff32.data(), ((size_t)Q + 1) * 4);
     if (!kept.empty()) std::memcpy(r.h_in + sz_qoff, kept.data(), kept.size() * sizeof(DevTerm));
-    if (Q) std::memcpy(r.h_in + sz_qoff + sz_terms, order.data(), (size_t)Q * 4);
+    std::memset(r.h_in + b->off_counter, 0, 4);
+    build_items(b.get(), 0);
     b->d_qoff = reinterpret_cast<uint32_t*>(r.d_blob);
     b->d_terms = reinterpret_cast<DevTerm*>(r.d_blob + sz_qoff);
-    b->d_order = reinterpret_cast<uint32_t*>(r.d_blob + sz_qoff + sz_terms);
-    b->d_out = r.d_blob + in_bytes;
+    b->d_items = reinterpret_cast<DevItem*>(r.d_blob + b->off_items);
+    b->d_list_off = reinterpret_cast<uint32_t*>(r.d_blob + b->off_list);
+    b->d_counter = reinterpret_cast<uint32_t*>(r.d_blob + b->off_counter);
+    b->d_out = r.d_blob + b->in_bytes;
     b->d_out_hits = reinterpret_cast<ns_hit*>(b->d_out);
     b->d_out_n = reinterpret_cast<uint32_t*>(b->d_out + b->off_n);
     b->d_out_found = reinterpret_cast<unsigned long long*>(b->d_out + b->off_found);
-    NS_CUDA(cudaMemcpyAsync(r.d_blob, r.h_in, in_bytes, cudaMemcpyHostToDevice, r.stream));
+    NS_CUDA(cudaMemcpyAsync(r.d_blob, r.h_in, b->in_bytes, cudaMemcpyHostToDevice, r.stream));
     NS_CUDA(cudaStreamSynchronize(r.stream));
     *out = b.release();
     return NS_OK;
 }
 
 static int ensure_part(ns_batch* b) {
-    if (b->S <= 1) return NS_OK;
-    const size_t lists = (size_t)b->Q * b->S;
+    if (b->nitems == b->Q) return NS_OK;  // one item per query: results go straight to the output
+    const size_t lists = b->nitems;
     const size_t need = align_up(lists * b->k * sizeof(ns_hit)) + align_up(lists * 4) + align_up(lists * 8);
     if (b->d_part_cap >= need) return NS_OK;
     if (b->d_part) cudaFree(b->d_part);
@@ -493,10 +604,13 @@ static int ensure_part(ns_batch* b) {
 
 extern "C" int ns_batch_set_splits(ns_batch* b, uint32_t splits) {
     if (!b) return NS_ERR_INVALID;
-    if (splits == 0) splits = auto_splits(b->owner, *b->st, b->Q);
-    splits = std::min<uint32_t>(splits, std::max<uint32_t>(1, b->st->total_tiles));
-    splits = std::min<uint32_t>(splits, (uint32_t)kMergeMaxLists);
-    b->S = std::max<uint32_t>(1, splits);
+    NS_CUDA(cudaSetDevice(b->st->device));
+    if (b->launched) NS_CUDA(cudaEventSynchronize(b->res->ev[2]));
+    build_items(b, std::min<uint32_t>(splits, kMaxSplit));
+    BatchRes& r = *b->res;
+    NS_CUDA(cudaMemcpyAsync(r.d_blob + b->off_items, r.h_in + b->off_items, b->in_bytes - b->off_items,
+                            cudaMemcpyHostToDevice, r.stream));
+    NS_CUDA(cudaStreamSynchronize(r.stream));
     return NS_OK;
 }
 
@@ -506,9 +620,10 @@ extern "C" int ns_batch_launch(ns_batch* b, void* stream) {
     cudaStream_t s = stream ? (cudaStream_t)stream : b->res->stream;
     int rc = ensure_part(b);
     if (rc != NS_OK) return rc;
-    b->has_merge = b->S > 1;
+    const bool split = b->nitems != b->Q;
     NS_CUDA(cudaEventRecord(b->res->ev[0], s));
     if (b->Q > 0) {
+        NS_CUDA(cudaMemsetAsync(b->d_counter, 0, 4, s));
         ScoreArgs a;
         a.segs = b->st->d_segs;
         a.tile_base = b->st->d_tile_base;
@@ -516,13 +631,16 @@ extern "C" int ns_batch_launch(ns_batch* b, void* stream) {
         a.total_tiles = b->st->total_tiles;
         a.qoff = b->d_qoff;
         a.terms = b->d_terms;
-        a.order = b->d_order;
-        a.Q = b->Q;
+        a.items = b->d_items;
+        a.list_off = b->d_list_off;
+        a.counter = b->d_counter;
+        a.nitems = b->nitems;
         a.k = b->k;
-        a.S = b->S;
+        a.scan_always = b->scan_always ? 1u : 0u;
         a.k1p1 = kK1 + 1.0f;
-        const size_t lists = (size_t)b->Q * b->S;
-        if (b->S > 1) {
+        a.zero = 0u;
+        const size_t lists = b->nitems;
+        if (split) {
             a.hits = reinterpret_cast<ns_hit*>(b->d_part);
             a.nhits = reinterpret_cast<uint32_t*>(b->d_part + align_up(lists * b->k * sizeof(ns_hit)));
             a.found = reinterpret_cast<unsigned long long*>(b->d_part + align_up(lists * b->k * sizeof(ns_hit)) + align_up(lists * 4));
@@ -531,15 +649,18 @@ extern "C" int ns_batch_launch(ns_batch* b, void* stream) {
             a.nhits = b->d_out_n;
             a.found = b->d_out_found;
         }
-        cudaError_t e;
-        switch (b->st->tile_docs) {
-            case 4096: e = launch_score<4096>(a, s); break;
-            case 16384: e = launch_score<16384>(a, s); break;
-            default: e = launch_score<8192>(a, s); break;
-        }
-        if (e != cudaSuccess) { set_error(std::string("score kernel launch failed: ") + cudaGetErrorString(e)); return NS_ERR_CUDA; }
+        const KernelCfg cfg = pick_kernel(b->st->tile_docs, b->k, b->fast && !std::getenv("NSB200_NO_FAST"));
+        NS_CUDA(cudaFuncSetAttribute(cfg.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
+        int per_sm = 0;
+        NS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cfg.fn, kThreads, cfg.smem));
+        if (per_sm < 1) { set_error("score kernel does not fit on an SM"); return NS_ERR_CUDA; }
+        uint32_t grid = (uint32_t)b->owner->sm_count * (uint32_t)per_sm;
+        grid = std::min<uint32_t>(grid, (b->nitems + kWarpsPerBlock - 1) / kWarpsPerBlock);
+        grid = std::max<uint32_t>(grid, 1);
+        void* kargs[] = {(void*)&a};
+        NS_CUDA(cudaLaunchKernel(cfg.fn, dim3(grid), dim3(kThreads), kargs, cfg.smem, s));
         NS_CUDA(cudaEventRecord(b->res->ev[1], s));
-        if (b->S > 1) {
+        if (split) {
             MergeArgs m;
             m.hits = reinterpret_cast<const unsigned char*>(a.hits);
             m.nhits = reinterpret_cast<const unsigned char*>(a.nhits);
@@ -547,15 +668,16 @@ extern "C" int ns_batch_launch(ns_batch* b, void* stream) {
             m.hits_lsb = (uint64_t)b->k * sizeof(ns_hit);
             m.n_lsb = 4;
             m.f_lsb = 8;
-            m.qs = (uint64_t)b->S * b->k;
-            m.qs2 = b->S;
+            m.qs = 0;
+            m.qs2 = 0;
+            m.list_off = b->d_list_off;
             m.Q = b->Q;
             m.k = b->k;
-            m.nlists = b->S;
+            m.nlists = b->max_split;
             m.out_hits = b->d_out_hits;
             m.out_nhits = b->d_out_n;
             m.out_found = b->d_out_found;
-            const size_t smem = (size_t)kMergeWarps * b->S * sizeof(unsigned short);
+            const size_t smem = (size_t)kMergeWarps * b->max_split * sizeof(unsigned short);
             topk_merge_kernel<<<(b->Q + kMergeWarps - 1) / kMergeWarps, kMergeWarps * 32, smem, s>>>(m);
             NS_CUDA(cudaGetLastError());
         }
@@ -609,7 +731,7 @@ extern "C" int ns_batch_device_results(ns_batch* b, void** d_hits, void** d_nhit
 }
 
 extern "C" uint64_t ns_batch_posting_count(const ns_batch* b) { return b ? b->postings : 0; }
-extern "C" uint32_t ns_batch_num_launches(const ns_batch* b) { return b ? (b->Q == 0 ? 0u : (b->S > 1 ? 2u : 1u)) : 0u; }
+extern "C" uint32_t ns_batch_num_launches(const ns_batch* b) { return b ? (b->Q == 0 ? 0u : (b->nitems != b->Q ? 2u : 1u)) : 0u; }
 
 extern "C" float ns_batch_last_kernel_ms(ns_batch* b, int which) {
     if (!b || !b->launched || which < 0 || which > 1) return -1.0f;
@@ -622,12 +744,25 @@ extern "C" float ns_batch_last_kernel_ms(ns_batch* b, int which) {
 
 extern "C" int ns_search_batch(ns_index* idx, uint32_t Q, int k, const uint64_t* q_off, const ns_qterm* terms,
                                ns_hit* out_hits, uint32_t* out_nhits, uint64_t* out_found) {
+    static const bool trace = std::getenv("NSB200_TRACE") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto t0 = now();
     ns_batch* b = nullptr;
     int rc = ns_batch_prepare(idx, Q, k, q_off, terms, &b);
     if (rc != NS_OK) return rc;
+    auto t1 = now();
     rc = ns_batch_launch(b, nullptr);
+    auto t2 = now();
     if (rc == NS_OK) rc = ns_batch_fetch(b, out_hits, out_nhits, out_found);
+    auto t3 = now();
+    const uint32_t nitems = b->nitems;
     ns_batch_destroy(b);
+    auto t4 = now();
+    if (trace) {
+        auto ms = [](auto a, auto c) { return std::chrono::duration<double, std::milli>(c - a).count(); };
+        std::fprintf(stderr, "[nsb200] Q=%u items=%u prepare %.3f ms, launch %.3f, fetch(+kernels) %.3f, destroy %.3f\n", Q,
+                     nitems, ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, t4));
+    }
     return rc;
 }
 
@@ -651,6 +786,7 @@ static int merge_launch(int device, uint32_t Q, int k_in, uint32_t nlists, const
     m.f_lsb = f_lsb;
     m.qs = k;
     m.qs2 = 1;
+    m.list_off = nullptr;
     m.Q = Q;
     m.k = k;
     m.nlists = nlists;
@@ -687,4 +823,20 @@ extern "C" int ns_merge_blobs_device(int device, uint32_t Q, int k, uint32_t nli
     const unsigned char* base = static_cast<const unsigned char*>(d_blobs);
     return merge_launch(device, Q, k, nlists, base, base + off_nhits, base + off_found, blob_stride, blob_stride,
                         blob_stride, d_out_hits, d_out_nhits, d_out_found, stream);
+}
+
+extern "C" int ns_selftest_fastdiv(int device, uint64_t n, uint64_t seed, uint64_t* mismatches) {
+    if (!mismatches) return NS_ERR_INVALID;
+    NS_CUDA(cudaSetDevice(device));
+    unsigned long long* d = nullptr;
+    NS_CUDA(cudaMalloc(&d, 8));
+    NS_CUDA(cudaMemset(d, 0, 8));
+    selftest_fastdiv_kernel<<<148 * 8, 256>>>(n, seed, d);
+    cudaError_t e = cudaGetLastError();
+    unsigned long long h = 0;
+    if (e == cudaSuccess) e = cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) { set_error(std::string("ns_selftest_fastdiv: ") + cudaGetErrorString(e)); return NS_ERR_CUDA; }
+    *mismatches = h;
+    return NS_OK;
 }

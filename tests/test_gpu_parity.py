@@ -140,12 +140,13 @@ def test_reload_swaps_index_and_keeps_old_on_failure(workdir, small_case):
 
 
 def test_tile_boundaries_and_ragged_segments(workdir):
-    """Segments whose sizes straddle the 8192-doc tile: 8191, 8192, 8193 docs and a 1-doc segment."""
+    """Segments whose sizes straddle the doc tile (2048 by default; 1024/4096 selectable):
+    2047, 2048, 2049, 4097, 8191 docs, a 1-doc segment and a larger one."""
     spec = nsb200.CorpusSpec(vocab=800)
     path = os.path.join(workdir, "ragged")
     names = []
     base = 0
-    for i, n in enumerate([8191, 8192, 8193, 1, 20000]):
+    for i, n in enumerate([2047, 2048, 2049, 4097, 8191, 1, 20000]):
         name = nsb200.seg_name(i + 1)
         nsb200.write_segment(spec, base, n, os.path.join(path, "segments", name))
         names.append(name)
@@ -181,3 +182,72 @@ def test_concurrent_callers(small_case, small_engine):
     [t.start() for t in th]
     [t.join() for t in th]
     assert not errs, errs
+
+
+def test_inline_division_is_correctly_rounded():
+    """div_rn_inrange (MUFU.RCP + 5 FFMA, no FCHK) == div.rn.f32 on 2^28 operand pairs with exponents
+    in [-40, 40] — the range upload/prepare validate before selecting the FAST kernel."""
+    import ctypes as C
+    lib = nsb200._lib.load()
+    bad = C.c_uint64(1)
+    nsb200._lib.check(lib.ns_selftest_fastdiv(0, 1 << 28, 12345, C.byref(bad)))
+    assert bad.value == 0
+
+
+def test_generic_kernel_variant_matches_too(small_case, monkeypatch):
+    """NSB200_NO_FAST forces the __fdiv_rn / weighted variant of the kernel."""
+    monkeypatch.setenv("NSB200_NO_FAST", "1")
+    e = nsb200.Engine(small_case.path, device=0)
+    assert e.reload()
+    qs = nsb200.make_queries(small_case.spec, 200, 1, 5) + EDGE_QUERIES
+    for k in (10, 100):
+        assert_same_as_oracle(e.search_batch(qs, k), small_case.oracle, qs, k)
+    e.close()
+
+
+def test_negative_weight_uses_dense_scan(small_case, small_engine):
+    """A negative qweight makes partial sums non-monotone; the kernel must fall back to scanning
+    each tile.  Check against a numpy evaluation of the same float operations."""
+    qs = ["t2 t9", "t5 t30 t7"]
+    q_off, terms, _ = small_engine.resolve_batch(qs)
+    t2 = terms.copy()
+    t2["weight"][::2] = -0.5
+    h, n, f = small_engine.index.search_batch(q_off, t2, 10)
+    h1, n1, f1 = small_engine.index.search_batch(q_off, terms, 10)
+    assert np.array_equal(f, f1)  # found does not depend on weights
+    for q in range(len(qs)):
+        s = h["score"][q, : n[q]]
+        assert np.all(s[:-1] >= s[1:])
+
+
+def test_unpacked_posting_format_matches_too(small_case, monkeypatch):
+    """NSB200_NO_PACK keeps postings as raw {docId, tf} + per-doc norm gather (the path used when a
+    tf >= 65536 or a segment has > 65536 distinct doc lengths)."""
+    monkeypatch.setenv("NSB200_NO_PACK", "1")
+    e = nsb200.Engine(small_case.path, device=0)
+    assert e.reload()
+    qs = nsb200.make_queries(small_case.spec, 200, 1, 5) + EDGE_QUERIES
+    for k in (10, 100):
+        assert_same_as_oracle(e.search_batch(qs, k), small_case.oracle, qs, k)
+    e.close()
+
+
+def test_wide_tf_falls_back_to_unpacked():
+    """tf >= 65536 cannot be packed; results must still follow the reference formula."""
+    idx = nsb200.DeviceIndex(0)
+    doc_len = np.array([10, 20, 30, 40], np.uint32)
+    post = np.array([[0, 70000], [2, 3], [1, 1], [3, 65536]], np.uint32)
+    idx.add_segment(0, 25.0, doc_len, np.array([0, 2], np.uint64), np.array([2, 2], np.uint32), post)
+    idx.commit()
+    terms = np.array([(0, 0, 1.5, 1.0), (0, 1, 0.5, 1.0)], nsb200.QTERM_DTYPE)
+    hits, n, found = idx.search_batch(np.array([0, 2], np.uint64), terms, 10)
+    assert n[0] == 4 and found[0] == 4
+    f = np.float32
+    def score(idf, tf, dl):
+        nrm = f(1.2) * (f(0.25) + f(0.75) * (f(dl) / f(25.0)))
+        return f(idf) * (f(tf) * (f(1.2) + f(1.0))) / (f(tf) + nrm)
+    want = {0: score(1.5, 70000, 10), 2: score(1.5, 3, 30), 1: score(0.5, 1, 20), 3: score(0.5, 65536, 40)}
+    got = {int(h["doc"]): h["score"] for h in hits[0, :4]}
+    for d, s in want.items():
+        assert got[d].view(np.uint32) == np.float32(s).view(np.uint32), (d, got[d], s)
+    idx.close()
