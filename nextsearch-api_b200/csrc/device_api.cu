@@ -110,6 +110,7 @@ struct ns_index {
     std::shared_ptr<IndexState> live;
     std::vector<SegState> staged;
     std::vector<std::unique_ptr<BatchRes>> pool;
+    std::unordered_map<const void*, int> occupancy;  // kernel variant -> resident CTAs per SM
     int sm_count = 148;
 };
 
@@ -246,7 +247,7 @@ extern "C" int ns_index_add_segment(ns_index* idx, uint32_t global_seg, uint32_t
 
     const size_t tile_entries = (size_t)T * (s.ntiles + 1);
     const size_t nlen = can_pack ? uniq.size() : (size_t)N;  // lengths the norm kernel evaluates
-    NS_CUDA_SEG(cudaMalloc(&s.d_post, std::max<size_t>(16, P * sizeof(uint2))));
+    NS_CUDA_SEG(cudaMalloc(&s.d_post, (P + 2) * sizeof(uint2)));  // +2: bulk copies round slices up to 16 B
     NS_CUDA_SEG(cudaMalloc(&s.d_tileoff, std::max<size_t>(16, tile_entries * sizeof(uint32_t))));
     NS_CUDA_SEG(cudaMalloc(&d_len, std::max<size_t>(16, nlen * 4)));
     NS_CUDA_SEG(cudaMalloc(&d_begin, std::max<size_t>(16, (size_t)T * 4)));
@@ -649,10 +650,22 @@ extern "C" int ns_batch_launch(ns_batch* b, void* stream) {
             a.nhits = b->d_out_n;
             a.found = b->d_out_found;
         }
-        const KernelCfg cfg = pick_kernel(b->st->tile_docs, b->k, b->fast && !std::getenv("NSB200_NO_FAST"));
-        NS_CUDA(cudaFuncSetAttribute(cfg.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
+        static const bool no_fast = std::getenv("NSB200_NO_FAST") != nullptr;
+        const KernelCfg cfg = pick_kernel(b->st->tile_docs, b->k, b->fast && !no_fast);
+        // the smem opt-in and the occupancy query cost ~0.4 ms of host time per call: once per
+        // (device, kernel variant)
         int per_sm = 0;
-        NS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cfg.fn, kThreads, cfg.smem));
+        {
+            std::lock_guard<std::mutex> lk(b->owner->mu);
+            auto it = b->owner->occupancy.find(cfg.fn);
+            if (it == b->owner->occupancy.end()) {
+                NS_CUDA(cudaFuncSetAttribute(cfg.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
+                NS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cfg.fn, kThreads, cfg.smem));
+                b->owner->occupancy[cfg.fn] = per_sm;
+            } else {
+                per_sm = it->second;
+            }
+        }
         if (per_sm < 1) { set_error("score kernel does not fit on an SM"); return NS_ERR_CUDA; }
         uint32_t grid = (uint32_t)b->owner->sm_count * (uint32_t)per_sm;
         grid = std::min<uint32_t>(grid, (b->nitems + kWarpsPerBlock - 1) / kWarpsPerBlock);
