@@ -48,6 +48,7 @@ struct SegState {
     bool packed = false;
     uint32_t* d_tileoff = nullptr;
     std::vector<uint32_t> h_count;  // LexEntry.count per row (query weights, row validation)
+    std::vector<uint32_t> h_begin;  // first posting per row (impact pre-pass source ranges)
     uint64_t bytes = 0;
     bool norm_in_range = true;      // every norm[] value validated for div_rn_inrange
     void release() {
@@ -88,11 +89,14 @@ struct BatchRes {
     size_t h_in_cap = 0;
     uint8_t* h_out = nullptr;
     size_t h_out_cap = 0;
+    uint8_t* d_scratch = nullptr;  // per-batch impact array, grown on demand
+    size_t scratch_cap = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     ~BatchRes() {
         cudaSetDevice(device);
         if (d_blob) cudaFree(d_blob);
+        if (d_scratch) cudaFree(d_scratch);
         if (h_in) cudaFreeHost(h_in);
         if (h_out) cudaFreeHost(h_out);
         for (auto& e : ev)
@@ -122,6 +126,11 @@ struct ns_batch {
     uint32_t nitems = 0, max_split = 1;
     bool scan_always = false;
     bool fast = false;  // operand ranges validated + unit weights: FAST kernel variant
+    bool impact = false;           // per-batch shared term scores (impact pre-pass)
+    uint32_t ndist = 0;            // distinct (segment, row, idf) terms of the batch
+    uint64_t dist_postings = 0;    // postings the pre-pass evaluates
+    DevDistinct* d_dist = nullptr;
+    uint32_t* d_dstart = nullptr;
     uint64_t nterms = 0, postings = 0;
     std::vector<uint64_t> weight;  // postings per query (host copy, for re-splitting)
     // device sub-arrays of the input blob
@@ -169,7 +178,7 @@ extern "C" int ns_index_create(int device, ns_index** out) {
     idx->sm_count = prop.multiProcessorCount;
     if (const char* t = std::getenv("NSB200_TILE_DOCS")) {
         int v = std::atoi(t);
-        if (v == 1024 || v == 2048 || v == 4096) idx->tile_docs = (uint32_t)v;
+        if (v == 2048 || v == 4096) idx->tile_docs = (uint32_t)v;
     }
     *out = idx;
     return NS_OK;
@@ -210,6 +219,7 @@ extern "C" int ns_index_add_segment(ns_index* idx, uint32_t global_seg, uint32_t
     s.ntiles = (N + idx->tile_docs - 1) / idx->tile_docs;
     if (s.ntiles == 0) s.ntiles = 1;
     s.h_count.assign(term_count, term_count + T);
+    s.h_begin = begin32;
 
     // Distinct doc lengths -> 16-bit codes (packed payload).  Falls back to the per-doc norm array
     // when the segment has more than 65536 distinct lengths or (checked on the device) a tf >= 65536.
@@ -437,11 +447,17 @@ void build_items(ns_batch* b, uint32_t forced) {
     // small batches: cut finer so that every resident warp has work
     const uint64_t want_items = (uint64_t)b->owner->sm_count * 24 * 2;
     if (Q > 0 && b->postings / target + Q < want_items) target = std::max<uint64_t>(1024, b->postings / want_items);
+    // NSB200_WINDOW_TILES=w: tile-major order — every query is cut into windows of ~w tiles and
+    // items are ordered by window first, so that all resident warps sweep the same doc range of
+    // the index at the same time and the hot posting slices are served from L2.
+    uint32_t window = 0;
+    if (const char* s = std::getenv("NSB200_WINDOW_TILES")) window = (uint32_t)std::max(0, std::atoi(s));
     std::vector<uint32_t> nsplit(Q);
     std::vector<uint32_t> list_off((size_t)Q + 1, 0);
     uint32_t maxs = 1;
     for (uint32_t q = 0; q < Q; q++) {
         uint64_t ns = forced ? forced : (b->weight[q] + target - 1) / target;
+        if (!forced && window) ns = (tiles + window - 1) / window;
         ns = std::max<uint64_t>(1, std::min<uint64_t>(ns, std::min<uint64_t>(tiles, kMaxSplit)));
         nsplit[q] = (uint32_t)ns;
         maxs = std::max(maxs, nsplit[q]);
@@ -453,7 +469,14 @@ void build_items(ns_batch* b, uint32_t forced) {
     for (uint32_t q = 0; q < Q; q++)
         for (uint32_t sp = 0; sp < nsplit[q]; sp++)
             items.push_back({b->weight[q] / nsplit[q], DevItem{q, (sp << 16) | nsplit[q]}});
-    std::stable_sort(items.begin(), items.end(), [](const auto& x, const auto& y) { return x.first > y.first; });
+    if (window && !forced) {
+        std::stable_sort(items.begin(), items.end(), [](const auto& x, const auto& y) {
+            const uint32_t sx = x.second.split_ns >> 16, sy = y.second.split_ns >> 16;
+            return sx != sy ? sx < sy : x.first > y.first;
+        });
+    } else {
+        std::stable_sort(items.begin(), items.end(), [](const auto& x, const auto& y) { return x.first > y.first; });
+    }
     DevItem* h_items = reinterpret_cast<DevItem*>(b->res->h_in + b->off_items);
     for (uint32_t i = 0; i < nitems; i++) h_items[i] = items[i].second;
     std::memcpy(b->res->h_in + b->off_list, list_off.data(), ((size_t)Q + 1) * 4);
@@ -466,23 +489,21 @@ struct KernelCfg {
     size_t smem;
 };
 
-template <int TDW, int KCAP, bool FAST>
+template <int TDW, int KCAP, bool FAST, bool IMPACT>
 KernelCfg cfg_of() {
-    return KernelCfg{(const void*)bm25_score_topk_kernel<TDW, KCAP, FAST>, sizeof(WarpSmem<TDW, KCAP>) * kWarpsPerBlock};
+    return KernelCfg{(const void*)bm25_score_topk_kernel<TDW, KCAP, FAST, IMPACT>,
+                     sizeof(WarpSmem<TDW, KCAP>) * kWarpsPerBlock};
 }
 
-template <int TDW>
-KernelCfg pick_kernel_t(uint32_t k, bool fast) {
-    if (k <= 16) return fast ? cfg_of<TDW, 16, true>() : cfg_of<TDW, 16, false>();
-    return fast ? cfg_of<TDW, 104, true>() : cfg_of<TDW, 104, false>();
+template <int TDW, int KCAP>
+KernelCfg pick_kernel_tk(bool fast, bool impact) {
+    if (fast) return impact ? cfg_of<TDW, KCAP, true, true>() : cfg_of<TDW, KCAP, true, false>();
+    return impact ? cfg_of<TDW, KCAP, false, true>() : cfg_of<TDW, KCAP, false, false>();
 }
 
-KernelCfg pick_kernel(uint32_t tile_docs, uint32_t k, bool fast) {
-    switch (tile_docs) {
-        case 1024: return pick_kernel_t<1024>(k, fast);
-        case 4096: return pick_kernel_t<4096>(k, fast);
-        default: return pick_kernel_t<2048>(k, fast);
-    }
+KernelCfg pick_kernel(uint32_t tile_docs, uint32_t k, bool fast, bool impact) {
+    if (tile_docs == 4096) return k <= 16 ? pick_kernel_tk<4096, 16>(fast, impact) : pick_kernel_tk<4096, 104>(fast, impact);
+    return k <= 16 ? pick_kernel_tk<2048, 16>(fast, impact) : pick_kernel_tk<2048, 104>(fast, impact);
 }
 
 }  // namespace
@@ -504,6 +525,19 @@ extern "C" int ns_batch_prepare(ns_index* idx, uint32_t Q, int k_in, const uint6
     const uint64_t nin = q_off[Q];
     std::vector<DevTerm> kept;
     kept.reserve(nin);
+    struct DistKey {
+        uint64_t slot_row;
+        uint32_t idf_bits;
+        bool operator==(const DistKey& o) const { return slot_row == o.slot_row && idf_bits == o.idf_bits; }
+    };
+    struct DistHash {
+        size_t operator()(const DistKey& k) const { return (size_t)(k.slot_row * 0x9E3779B97F4A7C15ull ^ k.idf_bits); }
+    };
+    std::unordered_map<DistKey, uint32_t, DistHash> dist_of;
+    dist_of.reserve(nin);
+    std::vector<DevDistinct> dist;
+    std::vector<uint32_t> dstart;
+    uint64_t dist_post = 0;
     std::vector<uint32_t> qoff32((size_t)Q + 1, 0);
     auto b = std::make_unique<ns_batch>();
     b->weight.assign(Q, 0);
@@ -533,7 +567,19 @@ extern "C" int ns_batch_prepare(ns_index* idx, uint32_t Q, int k_in, const uint6
             if (!(t.weight >= 0.0f) || !(t.idf >= 0.0f)) scan_always = true;
             // FAST kernel: qweight == 1.0f and idf in [2^-40, 2^6] (see div_rn_inrange)
             if (t.weight != 1.0f || !(t.idf >= 9.094947017729282e-13f && t.idf <= 64.0f)) fast = false;
-            kept.push_back(DevTerm{slot, t.row, t.idf, t.weight});
+            // distinct (segment, row, idf): one evaluation of the term's scores per batch
+            uint32_t idf_bits;
+            std::memcpy(&idf_bits, &t.idf, 4);
+            const DistKey key{((uint64_t)slot << 32) | t.row, idf_bits};
+            auto ins = dist_of.emplace(key, (uint32_t)dist.size());
+            if (ins.second) {
+                if (dist_post + cnt >= 0xFFFFFF00ull) { set_error("ns_batch_prepare: batch touches >= 2^32 distinct postings"); return NS_ERR_INVALID; }
+                dist.push_back(DevDistinct{slot, sg.h_begin[t.row], (uint32_t)dist_post, t.idf});
+                dstart.push_back((uint32_t)dist_post);
+                dist_post += cnt;
+            }
+            const DevDistinct& dd = dist[ins.first->second];
+            kept.push_back(DevTerm{slot, t.row, t.idf, t.weight, dd.dst_begin - dd.src_begin, 0u});
             b->weight[q] += cnt;
         }
         if (kept.size() > 0xFFFFFFF0ull) { set_error("ns_batch_prepare: too many terms"); return NS_ERR_INVALID; }
@@ -549,6 +595,16 @@ extern "C" int ns_batch_prepare(ns_index* idx, uint32_t Q, int k_in, const uint6
     b->postings = total_post;
     b->scan_always = scan_always;
     b->fast = fast && !scan_always;
+    dstart.push_back((uint32_t)dist_post);
+    b->ndist = (uint32_t)dist.size();
+    b->dist_postings = dist_post;
+    // Share term scores across the batch when that removes enough evaluations: the pre-pass reads
+    // and writes every distinct posting once, the scoring kernel then skips ~2/3 of its arithmetic.
+    {
+        static const char* env = std::getenv("NSB200_IMPACT");
+        const double share = dist_post ? (double)total_post / (double)dist_post : 0.0;
+        b->impact = env ? (std::atoi(env) != 0 && dist_post > 0) : (share >= 1.5);
+    }
 
     const size_t tiles = std::max<uint32_t>(1, st->total_tiles);
     b->items_cap = (size_t)Q * std::min<size_t>(tiles, kMaxSplit);
@@ -557,10 +613,14 @@ extern "C" int ns_batch_prepare(ns_index* idx, uint32_t Q, int k_in, const uint6
     const size_t sz_items = align_up(std::max<size_t>(1, b->items_cap) * sizeof(DevItem));
     const size_t sz_list = align_up(((size_t)Q + 1) * 4);
     const size_t sz_counter = align_up(4);
+    const size_t sz_dist = align_up(std::max<size_t>(1, dist.size()) * sizeof(DevDistinct));
+    const size_t sz_dstart = align_up(dstart.size() * 4);
     b->off_items = sz_qoff + sz_terms;
     b->off_list = b->off_items + sz_items;
     b->off_counter = b->off_list + sz_list;
-    b->in_bytes = b->off_counter + sz_counter;
+    const size_t off_dist = b->off_counter + sz_counter;
+    const size_t off_dstart = off_dist + sz_dist;
+    b->in_bytes = off_dstart + sz_dstart;
     const size_t sz_hits = align_up(std::max<size_t>(1, (size_t)Q * k) * sizeof(ns_hit));
     const size_t sz_n = align_up(std::max<size_t>(1, Q) * 4);
     const size_t sz_found = align_up(std::max<size_t>(1, Q) * 8);
@@ -574,6 +634,22 @@ extern "C" int ns_batch_prepare(ns_index* idx, uint32_t Q, int k_in, const uint6
     std::memcpy(r.h_in, qoff32.data(), ((size_t)Q + 1) * 4);
     if (!kept.empty()) std::memcpy(r.h_in + sz_qoff, kept.data(), kept.size() * sizeof(DevTerm));
     std::memset(r.h_in + b->off_counter, 0, 4);
+    if (!dist.empty()) std::memcpy(r.h_in + off_dist, dist.data(), dist.size() * sizeof(DevDistinct));
+    std::memcpy(r.h_in + off_dstart, dstart.data(), dstart.size() * 4);
+    b->d_dist = reinterpret_cast<DevDistinct*>(r.d_blob + off_dist);
+    b->d_dstart = reinterpret_cast<uint32_t*>(r.d_blob + off_dstart);
+    if (b->impact) {
+        const size_t need = (dist_post + 4) * sizeof(uint2);
+        if (r.scratch_cap < need) {
+            if (r.d_scratch) cudaFree(r.d_scratch);
+            r.d_scratch = nullptr;
+            r.scratch_cap = 0;
+            size_t cap = 1 << 20;
+            while (cap < need) cap <<= 1;
+            NS_CUDA(cudaMalloc(&r.d_scratch, cap));
+            r.scratch_cap = cap;
+        }
+    }
     build_items(b.get(), 0);
     b->d_qoff = reinterpret_cast<uint32_t*>(r.d_blob);
     b->d_terms = reinterpret_cast<DevTerm*>(r.d_blob + sz_qoff);
@@ -640,6 +716,7 @@ extern "C" int ns_batch_launch(ns_batch* b, void* stream) {
         a.scan_always = b->scan_always ? 1u : 0u;
         a.k1p1 = kK1 + 1.0f;
         a.zero = 0u;
+        a.impacts = reinterpret_cast<const uint2*>(b->res->d_scratch);
         const size_t lists = b->nitems;
         if (split) {
             a.hits = reinterpret_cast<ns_hit*>(b->d_part);
@@ -651,7 +728,8 @@ extern "C" int ns_batch_launch(ns_batch* b, void* stream) {
             a.found = b->d_out_found;
         }
         static const bool no_fast = std::getenv("NSB200_NO_FAST") != nullptr;
-        const KernelCfg cfg = pick_kernel(b->st->tile_docs, b->k, b->fast && !no_fast);
+        const bool fast = b->fast && !no_fast;
+        const KernelCfg cfg = pick_kernel(b->st->tile_docs, b->k, fast, b->impact);
         // the smem opt-in and the occupancy query cost ~0.4 ms of host time per call: once per
         // (device, kernel variant)
         int per_sm = 0;
@@ -670,6 +748,21 @@ extern "C" int ns_batch_launch(ns_batch* b, void* stream) {
         uint32_t grid = (uint32_t)b->owner->sm_count * (uint32_t)per_sm;
         grid = std::min<uint32_t>(grid, (b->nitems + kWarpsPerBlock - 1) / kWarpsPerBlock);
         grid = std::max<uint32_t>(grid, 1);
+        if (b->impact) {
+            ImpactArgs ia;
+            ia.segs = b->st->d_segs;
+            ia.dist = b->d_dist;
+            ia.dstart = b->d_dstart;
+            ia.ndist = b->ndist;
+            ia.total = (uint32_t)b->dist_postings;
+            ia.impacts = reinterpret_cast<uint2*>(b->res->d_scratch);
+            ia.k1p1 = kK1 + 1.0f;
+            const uint64_t warps = (b->dist_postings + 127) / 128;
+            const uint32_t ig = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((warps + 7) / 8, (uint64_t)b->owner->sm_count * 8));
+            if (fast) impact_kernel<true><<<ig, 256, 0, s>>>(ia);
+            else impact_kernel<false><<<ig, 256, 0, s>>>(ia);
+            NS_CUDA(cudaGetLastError());
+        }
         void* kargs[] = {(void*)&a};
         NS_CUDA(cudaLaunchKernel(cfg.fn, dim3(grid), dim3(kThreads), kargs, cfg.smem, s));
         NS_CUDA(cudaEventRecord(b->res->ev[1], s));
@@ -744,7 +837,10 @@ extern "C" int ns_batch_device_results(ns_batch* b, void** d_hits, void** d_nhit
 }
 
 extern "C" uint64_t ns_batch_posting_count(const ns_batch* b) { return b ? b->postings : 0; }
-extern "C" uint32_t ns_batch_num_launches(const ns_batch* b) { return b ? (b->Q == 0 ? 0u : (b->nitems != b->Q ? 2u : 1u)) : 0u; }
+extern "C" uint32_t ns_batch_num_launches(const ns_batch* b) {
+    if (!b || b->Q == 0) return 0u;
+    return 1u + (b->impact ? 1u : 0u) + (b->nitems != b->Q ? 1u : 0u);
+}
 
 extern "C" float ns_batch_last_kernel_ms(ns_batch* b, int which) {
     if (!b || !b->launched || which < 0 || which > 1) return -1.0f;

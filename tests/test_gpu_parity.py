@@ -251,3 +251,16 @@ def test_wide_tf_falls_back_to_unpacked():
     for d, s in want.items():
         assert got[d].view(np.uint32) == np.float32(s).view(np.uint32), (d, got[d], s)
     idx.close()
+
+
+@pytest.mark.parametrize("impact", ["0", "1"])
+def test_impact_prepass_on_and_off(small_case, monkeypatch, impact):
+    """NSB200_IMPACT=1 shares each distinct term's BM25 scores across the batch (pre-pass kernel);
+    =0 evaluates them per (query, posting).  Both must be bit-identical to the oracle."""
+    monkeypatch.setenv("NSB200_IMPACT", impact)
+    e = nsb200.Engine(small_case.path, device=0)
+    assert e.reload()
+    qs = nsb200.make_queries(small_case.spec, 300, 1, 5) + EDGE_QUERIES
+    for k in (10, 100):
+        assert_same_as_oracle(e.search_batch(qs, k), small_case.oracle, qs, k)
+    e.close()
