@@ -450,7 +450,7 @@ void build_items(ns_batch* b, uint32_t forced) {
     // NSB200_WINDOW_TILES=w: tile-major order — every query is cut into windows of ~w tiles and
     // items are ordered by window first, so that all resident warps sweep the same doc range of
     // the index at the same time and the hot posting slices are served from L2.
-    uint32_t window = 0;
+    uint32_t window = 16;  // measured best on 1M docs x 4096 queries (profiles/r1_v4_summary.md); 0 = query-major
     if (const char* s = std::getenv("NSB200_WINDOW_TILES")) window = (uint32_t)std::max(0, std::atoi(s));
     std::vector<uint32_t> nsplit(Q);
     std::vector<uint32_t> list_off((size_t)Q + 1, 0);
@@ -612,7 +612,7 @@ extern "C" int ns_batch_prepare(ns_index* idx, uint32_t Q, int k_in, const uint6
     const size_t sz_terms = align_up(std::max<size_t>(1, kept.size()) * sizeof(DevTerm));
     const size_t sz_items = align_up(std::max<size_t>(1, b->items_cap) * sizeof(DevItem));
     const size_t sz_list = align_up(((size_t)Q + 1) * 4);
-    const size_t sz_counter = align_up(4);
+    const size_t sz_counter = align_up(4 + (size_t)Q * 4);  // work-queue head + qthr[Q], zeroed per launch
     const size_t sz_dist = align_up(std::max<size_t>(1, dist.size()) * sizeof(DevDistinct));
     const size_t sz_dstart = align_up(dstart.size() * 4);
     b->off_items = sz_qoff + sz_terms;
@@ -633,7 +633,7 @@ extern "C" int ns_batch_prepare(ns_index* idx, uint32_t Q, int k_in, const uint6
     BatchRes& r = *b->res;
     std::memcpy(r.h_in, qoff32.data(), ((size_t)Q + 1) * 4);
     if (!kept.empty()) std::memcpy(r.h_in + sz_qoff, kept.data(), kept.size() * sizeof(DevTerm));
-    std::memset(r.h_in + b->off_counter, 0, 4);
+    std::memset(r.h_in + b->off_counter, 0, 4 + (size_t)Q * 4);
     if (!dist.empty()) std::memcpy(r.h_in + off_dist, dist.data(), dist.size() * sizeof(DevDistinct));
     std::memcpy(r.h_in + off_dstart, dstart.data(), dstart.size() * 4);
     b->d_dist = reinterpret_cast<DevDistinct*>(r.d_blob + off_dist);
@@ -700,7 +700,7 @@ extern "C" int ns_batch_launch(ns_batch* b, void* stream) {
     const bool split = b->nitems != b->Q;
     NS_CUDA(cudaEventRecord(b->res->ev[0], s));
     if (b->Q > 0) {
-        NS_CUDA(cudaMemsetAsync(b->d_counter, 0, 4, s));
+        NS_CUDA(cudaMemsetAsync(b->d_counter, 0, 4 + (size_t)b->Q * 4, s));
         ScoreArgs a;
         a.segs = b->st->d_segs;
         a.tile_base = b->st->d_tile_base;
@@ -711,6 +711,7 @@ extern "C" int ns_batch_launch(ns_batch* b, void* stream) {
         a.items = b->d_items;
         a.list_off = b->d_list_off;
         a.counter = b->d_counter;
+        a.qthr = b->d_counter + 1;
         a.nitems = b->nitems;
         a.k = b->k;
         a.scan_always = b->scan_always ? 1u : 0u;
