@@ -169,9 +169,8 @@ def ref_search(index_dir: str, queries: Sequence[str], k: int, want_results: boo
     with tempfile.TemporaryDirectory() as td:
         qf = os.path.join(td, "q.txt")
         with open(qf, "w") as f:
-            for q in queries:
-                assert "\n" not in q
-                f.write(q + "\n")
+            for q in queries:  # one per line; the driver unescapes \\n and \\\\
+                f.write(q.replace("\\", "\\\\").replace("\n", "\\n") + "\n")
         out = os.path.join(td, "out.jsonl") if want_results else "-"
         r = subprocess.run([REF_ENGINE, "search", index_dir, qf, str(k), out], check=True, capture_output=True,
                            text=True, timeout=timeout)

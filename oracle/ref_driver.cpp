@@ -65,6 +65,20 @@ static int mode_write(const char* dump, const char* segdir) {
     return 0;
 }
 
+// query files are one query per line; "\\n" and "\\\\" escape a newline and a backslash
+static std::string unescape(const std::string& s) {
+    std::string o;
+    for (size_t i = 0; i < s.size(); i++) {
+        if (s[i] == '\\' && i + 1 < s.size()) {
+            o.push_back(s[i + 1] == 'n' ? '\n' : s[i + 1]);
+            i++;
+        } else {
+            o.push_back(s[i]);
+        }
+    }
+    return o;
+}
+
 static int mode_search(int argc, char** argv) {
     std::string index_dir = fs::absolute(argv[2]).string();
     std::string qfile = fs::absolute(argv[3]).string();
@@ -80,7 +94,7 @@ static int mode_search(int argc, char** argv) {
         std::string line;
         long i = 0;
         while (std::getline(in, line)) {
-            if (i >= first && (count < 0 || i < first + count)) queries.push_back(line);
+            if (i >= first && (count < 0 || i < first + count)) queries.push_back(unescape(line));
             i++;
         }
     }

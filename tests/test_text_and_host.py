@@ -1,0 +1,128 @@
+"""Host side of the path without a GPU: tokenizer, segment loader, lexicon resolve, error behaviour."""
+import os
+import shutil
+
+import numpy as np
+import pytest
+
+import fmt
+import nsb200
+from oracle import oracle as orc
+
+CASES = [
+    ("T7, the t9!", ["t7", "t9"]),
+    ("t3 t3", ["t3", "t3"]),                  # duplicates kept, order kept
+    ("the of and", []),
+    ("a b c", []),                            # len < 2
+    ("COVID-19 vaccine_trial", ["covid", "19", "vaccine", "trial"]),
+    ("café résumés", ["caf", "sum"]),   # bytes >= 0x80 separate tokens ("r" is too short)
+    ("  x1\ty2\nz3  ", ["x1", "y2", "z3"]),
+    ("from at this that it be been were was are is as by with on for in to of or and an a the", []),
+    ("", []),
+]
+
+
+@pytest.mark.parametrize("query,want", CASES)
+def test_query_terms_product_and_oracle(query, want):
+    assert nsb200.query_terms(query) == want
+    assert orc.query_terms(query) == want
+
+
+def test_loader_agrees_with_oracle_loader(small_case):
+    e = nsb200.Engine(small_case.path, device=None)
+    assert e.reload() is True
+    oi = small_case.oracle
+    assert e.num_segments == oi.num_segments == 2
+    assert e.seg_names == [oi.segment_name(i) for i in range(2)] == ["seg_000001", "seg_000002"]
+    for i in range(2):
+        a, b = e.segment_stats(i), oi.segment_stats(i)
+        assert a["N"] == b["N"] and a["T"] == b["T"] and a["P"] == b["P"]
+        assert np.float32(a["avgdl"]) == np.float32(b["avgdl"])
+        for term in ("t1", "t17", "t2999", "nosuch"):
+            assert e.term_stats(i, term) == oi.term_stats(i, term)
+        assert e.cord_uid(i, 7) == oi.cord_uid(i, 7) == f"uid{i * 1500 + 7}"
+    e.close()
+
+
+def test_resolve_batch_emits_reference_lookup(small_case):
+    """(segment asc, query order), duplicates kept, absent terms skipped, idf = bm25_idf(N, df)."""
+    e = nsb200.Engine(small_case.path, device=None)
+    assert e.reload()
+    qs = ["t3 t3 nosuch t5", "the of", "zz", "t1"]
+    q_off, terms, has = e.resolve_batch(qs)
+    assert list(has) == [True, False, True, True]
+    assert list(q_off) == [0, 6, 6, 6, 8]
+    assert list(terms["seg"][:6]) == [0, 0, 0, 1, 1, 1]
+    assert terms["row"][0] == terms["row"][1] != terms["row"][2]
+    assert np.all(terms["weight"] == 1.0)
+    for i in range(2):
+        N = e.segment_stats(i)["N"]
+        df, _ = e.term_stats(i, "t3")
+        from test_known_answer import idf
+        assert terms["idf"][3 * i].view(np.uint32) == np.float32(idf(N, df)).view(np.uint32)
+    e.close()
+
+
+def test_host_only_engine_refuses_to_search(small_case):
+    e = nsb200.Engine(small_case.path, device=None)
+    assert e.reload()
+    with pytest.raises(nsb200._lib.NsError) as ei:
+        e.search("t1", 10)
+    assert ei.value.status == 6 and "no CPU search path" in str(ei.value)
+    e.close()
+
+
+def test_reload_returns_false_like_the_reference(workdir, small_case):
+    """Engine::reload returns false when there are no segments (src/api_engine.cpp:73) or a segment
+    file is missing (:82-85; every one of the 64 barrels must open, src/api_segment.cpp:75-86)."""
+    empty = os.path.join(workdir, "empty_index")
+    os.makedirs(empty, exist_ok=True)
+    e = nsb200.Engine(empty, device=None)
+    assert e.reload() is False
+    e.close()
+    broken = os.path.join(workdir, "broken_index")
+    shutil.copytree(small_case.path, broken)
+    os.remove(os.path.join(broken, "segments", "seg_000002", "inverted_b063.bin"))
+    e = nsb200.Engine(broken, device=None)
+    assert e.reload() is False and "inverted barrel 63" in e.last_error
+    e.close()
+
+
+def test_manifest_fallback_scans_segment_dirs(workdir, small_case):
+    """No manifest.bin -> sorted scan of segments/seg_* (src/api_engine.cpp:58-70)."""
+    path = os.path.join(workdir, "no_manifest")
+    shutil.copytree(small_case.path, path)
+    os.remove(os.path.join(path, "manifest.bin"))
+    e = nsb200.Engine(path, device=None)
+    assert e.reload() and e.seg_names == ["seg_000001", "seg_000002"]
+    assert orc.OracleIndex(path).num_segments == 2
+    e.close()
+
+
+def test_legacy_segment_layout_loads(workdir):
+    idx = os.path.join(workdir, "legacy_host")
+    fmt.write_segment(os.path.join(idx, "segments", "seg_000001"), fmt.handmade_docs(), legacy=True)
+    fmt.write_manifest(idx, ["seg_000001"])
+    e = nsb200.Engine(idx, device=None)
+    assert e.reload()
+    assert e.segment_stats(0)["T"] == 8 and e.term_stats(0, "alpha") == (6, 6)
+    e.close()
+
+
+def test_shard_ownership(small_case):
+    e = nsb200.Engine(small_case.path, device=None, rank=1, world=2)
+    assert e.reload() and e.num_segments == 2
+    q_off, terms, has = e.resolve_batch(["t1 t2"])
+    assert set(terms["seg"]) == {1}          # only segment 1 belongs to rank 1 of 2
+    with pytest.raises(nsb200._lib.NsError):
+        e.segment_stats(0)                    # not loaded on this rank
+    e.close()
+
+
+def test_query_generator_is_deterministic():
+    a = nsb200.make_queries(nsb200.SPEC_10K, 50, 1, 3, seed=7)
+    b = nsb200.make_queries(nsb200.SPEC_10K, 50, 1, 3, seed=7)
+    assert a == b and a != nsb200.make_queries(nsb200.SPEC_10K, 50, 1, 3, seed=8)
+    assert all(1 <= len(q.split()) <= 3 for q in a)
+    head = nsb200.make_queries(nsb200.SPEC_10K, 50, 1, 5, seed=7, head_ranks=150)
+    assert all(int(q.split()[0][1:]) <= 150 for q in head)
