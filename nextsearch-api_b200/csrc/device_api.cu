@@ -17,6 +17,7 @@
 #include "../../include/nextsearch_b200.h"
 #include "bm25_kernels.cuh"
 #include "host/common.hpp"
+#include "host/segment_io.hpp"
 
 using namespace nsb;
 
@@ -47,6 +48,8 @@ struct SegState {
     float* d_lut = nullptr;    // per distinct doc length (packed segments)
     bool packed = false;
     uint32_t* d_tileoff = nullptr;
+    uint2* d_imp = nullptr;    // resident impacts, same index space as d_post (nullptr: not built)
+    std::vector<uint32_t> h_idf_bits;  // per row: bits of bm25_idf(N, count) the resident impacts were built with
     std::vector<uint32_t> h_count;  // LexEntry.count per row (query weights, row validation)
     std::vector<uint32_t> h_begin;  // first posting per row (impact pre-pass source ranges)
     uint64_t bytes = 0;
@@ -56,6 +59,8 @@ struct SegState {
         if (d_norm) cudaFree(d_norm);
         if (d_lut) cudaFree(d_lut);
         if (d_tileoff) cudaFree(d_tileoff);
+        if (d_imp) cudaFree(d_imp);
+        d_imp = nullptr;
         d_post = nullptr;
         d_norm = nullptr;
         d_lut = nullptr;
@@ -127,6 +132,7 @@ struct ns_batch {
     bool scan_always = false;
     bool fast = false;  // operand ranges validated + unit weights: FAST kernel variant
     bool impact = false;           // per-batch shared term scores (impact pre-pass)
+    uint32_t max_in_seg = 0;       // most terms any (query, segment) has
     uint32_t ndist = 0;            // distinct (segment, row, idf) terms of the batch
     uint64_t dist_postings = 0;    // postings the pre-pass evaluates
     DevDistinct* d_dist = nullptr;
@@ -176,10 +182,6 @@ extern "C" int ns_index_create(int device, ns_index** out) {
     cudaDeviceProp prop;
     NS_CUDA(cudaGetDeviceProperties(&prop, device));
     idx->sm_count = prop.multiProcessorCount;
-    if (const char* t = std::getenv("NSB200_TILE_DOCS")) {
-        int v = std::atoi(t);
-        if (v == 2048 || v == 4096) idx->tile_docs = (uint32_t)v;
-    }
     *out = idx;
     return NS_OK;
 }
@@ -306,6 +308,35 @@ extern "C" int ns_index_add_segment(ns_index* idx, uint32_t global_seg, uint32_t
         NS_CUDA_SEG(cudaGetLastError());
     }
     s.packed = can_pack;
+    // Resident impacts: the term score of every posting under the row's own idf (src/api_engine.cpp:45-47
+    // with df = LexEntry.count, which is what every writer stores: include/segment_writer.hpp:147-149).
+    // A query term whose idf differs bit-wise from this one goes through the per-batch pre-pass instead.
+    float* d_idf = nullptr;
+    if (P && T && !std::getenv("NSB200_NO_RESIDENT")) {
+        std::vector<float> h_idf(T);
+        s.h_idf_bits.resize(T);
+        for (uint32_t t = 0; t < T; t++) {
+            h_idf[t] = bm25_idf(N, term_count[t]);
+            std::memcpy(&s.h_idf_bits[t], &h_idf[t], 4);
+        }
+        cudaError_t e1 = cudaMalloc(&d_idf, (size_t)T * 4);
+        if (e1 == cudaSuccess) e1 = cudaMalloc(&s.d_imp, (P + 2) * sizeof(uint2));
+        if (e1 == cudaSuccess) e1 = cudaMemcpy(d_idf, h_idf.data(), (size_t)T * 4, cudaMemcpyHostToDevice);
+        if (e1 == cudaSuccess) {
+            const int blocks = (int)std::min<uint64_t>(((uint64_t)T + 7) / 8, (uint64_t)idx->sm_count * 32);
+            build_impacts_kernel<<<blocks, 256>>>(s.d_post, d_begin, d_count, d_idf, T, d_normdst, can_pack ? 1u : 0u,
+                                                  kK1 + 1.0f, s.d_imp);
+            e1 = cudaGetLastError();
+            if (e1 == cudaSuccess) e1 = cudaDeviceSynchronize();
+        }
+        if (d_idf) cudaFree(d_idf);
+        if (e1 != cudaSuccess) {
+            set_error(std::string("CUDA error building resident impacts: ") + cudaGetErrorString(e1));
+            cleanup();
+            s.release();
+            return NS_ERR_CUDA;
+        }
+    }
     NS_CUDA_SEG(cudaMemcpy(h_errs, d_err, sizeof(h_errs), cudaMemcpyDeviceToHost));
     NS_CUDA_SEG(cudaDeviceSynchronize());
     const unsigned int h_err = h_errs[0];
@@ -318,7 +349,7 @@ extern "C" int ns_index_add_segment(ns_index* idx, uint32_t global_seg, uint32_t
                   " postings are out of order, duplicated or have docId >= N");
         return NS_ERR_FORMAT;
     }
-    s.bytes = P * sizeof(uint2) + (can_pack ? (uint64_t)uniq.size() * 4 : (uint64_t)N * 4) + tile_entries * 4;
+    s.bytes = (s.d_imp ? 2 : 1) * P * sizeof(uint2) + (can_pack ? (uint64_t)uniq.size() * 4 : (uint64_t)N * 4) + tile_entries * 4;
     std::lock_guard<std::mutex> lk(idx->mu);
     for (auto& o : idx->staged) {
         if (o.gseg == global_seg) {
@@ -358,6 +389,7 @@ extern "C" int ns_index_commit(ns_index* idx) {
         d.packed = s.packed ? 1u : 0u;
         d.pad_ = 0;
         d.tileoff = s.d_tileoff;
+        d.imp = s.d_imp;
         d.ndocs = s.ndocs;
         d.T = s.T;
         d.ntiles = s.ntiles;
@@ -489,21 +521,22 @@ struct KernelCfg {
     size_t smem;
 };
 
-template <int TDW, int KCAP, bool FAST, bool IMPACT>
+template <int TDW, int KCAP, bool FAST, bool IMPACT, int NG>
 KernelCfg cfg_of() {
-    return KernelCfg{(const void*)bm25_score_topk_kernel<TDW, KCAP, FAST, IMPACT>,
+    return KernelCfg{(const void*)bm25_score_topk_kernel<TDW, KCAP, FAST, IMPACT, NG>,
                      sizeof(WarpSmem<TDW, KCAP>) * kWarpsPerBlock};
 }
 
-template <int TDW, int KCAP>
+template <int TDW, int KCAP, int NG>
 KernelCfg pick_kernel_tk(bool fast, bool impact) {
-    if (fast) return impact ? cfg_of<TDW, KCAP, true, true>() : cfg_of<TDW, KCAP, true, false>();
-    return impact ? cfg_of<TDW, KCAP, false, true>() : cfg_of<TDW, KCAP, false, false>();
+    if (fast) return impact ? cfg_of<TDW, KCAP, true, true, NG>() : cfg_of<TDW, KCAP, true, false, NG>();
+    return impact ? cfg_of<TDW, KCAP, false, true, NG>() : cfg_of<TDW, KCAP, false, false, NG>();
 }
 
-KernelCfg pick_kernel(uint32_t tile_docs, uint32_t k, bool fast, bool impact) {
-    if (tile_docs == 4096) return k <= 16 ? pick_kernel_tk<4096, 16>(fast, impact) : pick_kernel_tk<4096, 104>(fast, impact);
-    return k <= 16 ? pick_kernel_tk<2048, 16>(fast, impact) : pick_kernel_tk<2048, 104>(fast, impact);
+// wide: some (query, segment) has more than 32 terms (two 32-term register groups per lane)
+KernelCfg pick_kernel(uint32_t k, bool fast, bool impact, bool wide) {
+    if (wide) return k <= 16 ? pick_kernel_tk<2048, 16, 2>(fast, impact) : pick_kernel_tk<2048, 104, 2>(fast, impact);
+    return k <= 16 ? pick_kernel_tk<2048, 16, 1>(fast, impact) : pick_kernel_tk<2048, 104, 1>(fast, impact);
 }
 
 }  // namespace
@@ -541,7 +574,8 @@ extern "C" int ns_batch_prepare(ns_index* idx, uint32_t Q, int k_in, const uint6
     std::vector<uint32_t> qoff32((size_t)Q + 1, 0);
     auto b = std::make_unique<ns_batch>();
     b->weight.assign(Q, 0);
-    uint64_t total_post = 0;
+    uint64_t total_post = 0, nonres_post = 0, n_resident = 0;
+    uint32_t max_in_seg = 0;
     bool scan_always = false;
     bool fast = true;
     for (auto& sg : st->segs) fast = fast && sg.norm_in_range;
@@ -562,14 +596,22 @@ extern "C" int ns_batch_prepare(ns_index* idx, uint32_t Q, int k_in, const uint6
             prev_slot = slot;
             const uint32_t cnt = sg.h_count[t.row];
             if (cnt == 0) continue;
+            max_in_seg = std::max(max_in_seg, in_seg + 1);
             if (++in_seg > NS_MAX_TERMS) { set_error("ns_batch_prepare: more than NS_MAX_TERMS terms for one (query, segment)"); return NS_ERR_INVALID; }
             // negative or NaN contribution: partial sums are not monotone -> dense scan per tile
             if (!(t.weight >= 0.0f) || !(t.idf >= 0.0f)) scan_always = true;
             // FAST kernel: qweight == 1.0f and idf in [2^-40, 2^6] (see div_rn_inrange)
             if (t.weight != 1.0f || !(t.idf >= 9.094947017729282e-13f && t.idf <= 64.0f)) fast = false;
-            // distinct (segment, row, idf): one evaluation of the term's scores per batch
             uint32_t idf_bits;
             std::memcpy(&idf_bits, &t.idf, 4);
+            if (sg.d_imp && sg.h_idf_bits[t.row] == idf_bits) {  // scores are resident: nothing to evaluate
+                kept.push_back(DevTerm{slot, t.row, t.idf, t.weight, 0u, 0u});
+                b->weight[q] += cnt;
+                n_resident++;
+                continue;
+            }
+            // distinct (segment, row, idf): one evaluation of the term's scores per batch
+            nonres_post += cnt;
             const DistKey key{((uint64_t)slot << 32) | t.row, idf_bits};
             auto ins = dist_of.emplace(key, (uint32_t)dist.size());
             if (ins.second) {
@@ -579,7 +621,7 @@ extern "C" int ns_batch_prepare(ns_index* idx, uint32_t Q, int k_in, const uint6
                 dist_post += cnt;
             }
             const DevDistinct& dd = dist[ins.first->second];
-            kept.push_back(DevTerm{slot, t.row, t.idf, t.weight, dd.dst_begin - dd.src_begin, 0u});
+            kept.push_back(DevTerm{slot, t.row, t.idf, t.weight, dd.dst_begin - dd.src_begin, 1u});
             b->weight[q] += cnt;
         }
         if (kept.size() > 0xFFFFFFF0ull) { set_error("ns_batch_prepare: too many terms"); return NS_ERR_INVALID; }
@@ -594,6 +636,7 @@ extern "C" int ns_batch_prepare(ns_index* idx, uint32_t Q, int k_in, const uint6
     b->nterms = kept.size();
     b->postings = total_post;
     b->scan_always = scan_always;
+    b->max_in_seg = max_in_seg;
     b->fast = fast && !scan_always;
     dstart.push_back((uint32_t)dist_post);
     b->ndist = (uint32_t)dist.size();
@@ -602,8 +645,8 @@ extern "C" int ns_batch_prepare(ns_index* idx, uint32_t Q, int k_in, const uint6
     // and writes every distinct posting once, the scoring kernel then skips ~2/3 of its arithmetic.
     {
         static const char* env = std::getenv("NSB200_IMPACT");
-        const double share = dist_post ? (double)total_post / (double)dist_post : 0.0;
-        b->impact = env ? (std::atoi(env) != 0 && dist_post > 0) : (share >= 1.5);
+        const double share = dist_post ? (double)nonres_post / (double)dist_post : 0.0;
+        b->impact = n_resident > 0 || (env ? (std::atoi(env) != 0 && dist_post > 0) : (share >= 1.5));
     }
 
     const size_t tiles = std::max<uint32_t>(1, st->total_tiles);
@@ -730,7 +773,7 @@ extern "C" int ns_batch_launch(ns_batch* b, void* stream) {
         }
         static const bool no_fast = std::getenv("NSB200_NO_FAST") != nullptr;
         const bool fast = b->fast && !no_fast;
-        const KernelCfg cfg = pick_kernel(b->st->tile_docs, b->k, fast, b->impact);
+        const KernelCfg cfg = pick_kernel(b->k, fast, b->impact, b->max_in_seg > 32u);
         // the smem opt-in and the occupancy query cost ~0.4 ms of host time per call: once per
         // (device, kernel variant)
         int per_sm = 0;
@@ -749,7 +792,7 @@ extern "C" int ns_batch_launch(ns_batch* b, void* stream) {
         uint32_t grid = (uint32_t)b->owner->sm_count * (uint32_t)per_sm;
         grid = std::min<uint32_t>(grid, (b->nitems + kWarpsPerBlock - 1) / kWarpsPerBlock);
         grid = std::max<uint32_t>(grid, 1);
-        if (b->impact) {
+        if (b->impact && b->ndist > 0) {
             ImpactArgs ia;
             ia.segs = b->st->d_segs;
             ia.dist = b->d_dist;
@@ -840,7 +883,7 @@ extern "C" int ns_batch_device_results(ns_batch* b, void** d_hits, void** d_nhit
 extern "C" uint64_t ns_batch_posting_count(const ns_batch* b) { return b ? b->postings : 0; }
 extern "C" uint32_t ns_batch_num_launches(const ns_batch* b) {
     if (!b || b->Q == 0) return 0u;
-    return 1u + (b->impact ? 1u : 0u) + (b->nitems != b->Q ? 1u : 0u);
+    return 1u + (b->impact && b->ndist > 0 ? 1u : 0u) + (b->nitems != b->Q ? 1u : 0u);
 }
 
 extern "C" float ns_batch_last_kernel_ms(ns_batch* b, int which) {

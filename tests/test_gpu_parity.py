@@ -194,9 +194,13 @@ def test_inline_division_is_correctly_rounded():
     assert bad.value == 0
 
 
-def test_generic_kernel_variant_matches_too(small_case, monkeypatch):
-    """NSB200_NO_FAST forces the __fdiv_rn / weighted variant of the kernel."""
+@pytest.mark.parametrize("resident", ["0", "1"])
+def test_generic_kernel_variant_matches_too(small_case, monkeypatch, resident):
+    """NSB200_NO_FAST forces the __fdiv_rn / weighted variant of the kernel (with and without the
+    resident impact array built at upload)."""
     monkeypatch.setenv("NSB200_NO_FAST", "1")
+    if resident == "0":
+        monkeypatch.setenv("NSB200_NO_RESIDENT", "1")
     e = nsb200.Engine(small_case.path, device=0)
     assert e.reload()
     qs = nsb200.make_queries(small_case.spec, 200, 1, 5) + EDGE_QUERIES
@@ -220,10 +224,13 @@ def test_negative_weight_uses_dense_scan(small_case, small_engine):
         assert np.all(s[:-1] >= s[1:])
 
 
-def test_unpacked_posting_format_matches_too(small_case, monkeypatch):
+@pytest.mark.parametrize("resident", ["0", "1"])
+def test_unpacked_posting_format_matches_too(small_case, monkeypatch, resident):
     """NSB200_NO_PACK keeps postings as raw {docId, tf} + per-doc norm gather (the path used when a
     tf >= 65536 or a segment has > 65536 distinct doc lengths)."""
     monkeypatch.setenv("NSB200_NO_PACK", "1")
+    if resident == "0":
+        monkeypatch.setenv("NSB200_NO_RESIDENT", "1")
     e = nsb200.Engine(small_case.path, device=0)
     assert e.reload()
     qs = nsb200.make_queries(small_case.spec, 200, 1, 5) + EDGE_QUERIES
@@ -255,12 +262,39 @@ def test_wide_tf_falls_back_to_unpacked():
 
 @pytest.mark.parametrize("impact", ["0", "1"])
 def test_impact_prepass_on_and_off(small_case, monkeypatch, impact):
-    """NSB200_IMPACT=1 shares each distinct term's BM25 scores across the batch (pre-pass kernel);
-    =0 evaluates them per (query, posting).  Both must be bit-identical to the oracle."""
+    """Without resident impacts: NSB200_IMPACT=1 shares each distinct term's BM25 scores across the
+    batch (pre-pass kernel); =0 evaluates them per (query, posting).  Both must be bit-identical to
+    the oracle."""
     monkeypatch.setenv("NSB200_IMPACT", impact)
+    monkeypatch.setenv("NSB200_NO_RESIDENT", "1")
     e = nsb200.Engine(small_case.path, device=0)
     assert e.reload()
     qs = nsb200.make_queries(small_case.spec, 300, 1, 5) + EDGE_QUERIES
     for k in (10, 100):
         assert_same_as_oracle(e.search_batch(qs, k), small_case.oracle, qs, k)
     e.close()
+
+
+def test_foreign_idf_mixes_resident_and_per_batch_scores(small_case, small_engine, monkeypatch):
+    """The resident impacts hold each row's score under bm25_idf(N, count).  A term that arrives with
+    any other idf (bit-wise) must be evaluated per batch instead; a batch may mix both kinds.
+    Reference for the comparison: an index uploaded without resident impacts, scoring on the fly."""
+    qs = nsb200.make_queries(small_case.spec, 200, 1, 5) + ["t3 t3", "t1 t2 t1"]
+    q_off, terms, _ = small_engine.resolve_batch(qs)
+    mixed = terms.copy()
+    mixed["idf"][::3] = np.nextafter(mixed["idf"][::3], np.float32(10.0))   # 1 ulp off: not resident
+    mixed["idf"][1::7] *= np.float32(0.75)
+    mixed["weight"][::5] = 0.5
+    monkeypatch.setenv("NSB200_NO_RESIDENT", "1")
+    monkeypatch.setenv("NSB200_IMPACT", "0")
+    plain = nsb200.Engine(small_case.path, device=0)
+    assert plain.reload()
+    for k in (10, 100):
+        h0, n0, f0 = plain.index.search_batch(q_off, mixed, k)
+        h1, n1, f1 = small_engine.index.search_batch(q_off, mixed, k)
+        assert np.array_equal(n0, n1) and np.array_equal(f0, f1)
+        for q in range(len(qs)):
+            n = int(n0[q])
+            assert np.array_equal(h0["score"][q, :n].view(np.uint32), h1["score"][q, :n].view(np.uint32)), qs[q]
+            assert np.array_equal(h0["doc"][q, :n], h1["doc"][q, :n]) and np.array_equal(h0["seg"][q, :n], h1["seg"][q, :n])
+    plain.close()

@@ -1,0 +1,3 @@
+set -x
+python -m pytest tests -m gpu -x -q 2>&1 | tail -5
+python bench.py --steps 30 --warmup 5 --profile-mode 2>/dev/null
