@@ -10,7 +10,7 @@
  * src/api_engine.cpp + src/api_segment.cpp (+ autocomplete/metadata/semantic objects) compiled
  * by oracle/Makefile, and tests/golden/ holds its outputs (tests/golden/make_golden.py is the
  * generating script).  tests/test_oracle_golden.py checks this file against those vectors, and
- * tests/test_oracle_vs_ref.py re-runs the live reference binary when it is present.
+ * tests/test_oracle_golden.py (-m ref cases) re-runs the live reference binary when it is present.
  *
  * Each function cites the reference lines it follows (paths relative to /root/reference).
  *
