@@ -2,7 +2,7 @@
 
 The generator and writer live in libnsb200.so (csrc/host/corpus.cpp); this module only names the
 workloads.  The reference's include/segment_writer.hpp:23-169 produces the same bytes for the same
-documents (tests/test_oracle_golden.py) but needs ~2.5 min and ~2 GB per 1M docs.
+documents (byte-for-byte test under tests/) but needs ~2.5 min and ~2 GB per 1M docs.
 """
 from __future__ import annotations
 
