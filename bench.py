@@ -345,16 +345,52 @@ def ours(args, rank, world, local_rank):
     else:
         def e2e_step(i):
             return searcher.search_batch(batches[i % nb], TOPK)
+    def run_e2e(callers):
+        """e2e_steps search_batch calls issued by `callers` host threads (ns_engine_search_batch is
+        thread-safe: while one call's kernels run, another call's tokenise/lexicon/prepare proceeds).
+        Every call copies its descriptors H2D and its results D2H.  Returns (seconds, last result)."""
+        last_box = [None]
+        if callers <= 1 or world > 1:
+            t0 = time.perf_counter()
+            for i in range(e2e_steps):
+                last_box[0] = e2e_step(i)
+            torch.cuda.synchronize(dev)
+            return time.perf_counter() - t0, last_box[0]
+        nxt = [0]
+        lock = threading.Lock()
+
+        def worker():
+            while True:
+                with lock:
+                    i = nxt[0]
+                    nxt[0] += 1
+                if i >= e2e_steps:
+                    return
+                r = e2e_step(i)
+                if i == e2e_steps - 1:
+                    last_box[0] = r
+
+        ths = [threading.Thread(target=worker) for _ in range(callers)]
+        t0 = time.perf_counter()
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        torch.cuda.synchronize(dev)
+        return time.perf_counter() - t0, last_box[0]
+
     for i in range(2):
         e2e_step(i)
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
-    t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        last = e2e_step(i)
-    torch.cuda.synchronize(dev)
-    e2e_s = time.perf_counter() - t0
+    e2e_single_s, last = run_e2e(1)
+    callers = 1 if world > 1 else max(1, args.e2e_callers)
+    if callers > 1:
+        run_e2e(callers)  # warm the extra callers' pooled buffers
+        e2e_s, last = run_e2e(callers)
+    else:
+        e2e_s = e2e_single_s
     if world > 1:
         t = torch.tensor([e2e_s], device=f"cuda:{dev}")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -375,7 +411,7 @@ def ours(args, rank, world, local_rank):
             lat.append(time.perf_counter() - t1)
         lat.sort()
         extra["p50_ms_single_query"] = 1e3 * lat[len(lat) // 2] if lat else None
-        extra["p50_ms_batch_e2e"] = 1e3 * e2e_s / e2e_steps
+        extra["p50_ms_batch_e2e"] = 1e3 * e2e_single_s / e2e_steps
         cpu_baseline, parity = cpu_baseline_leg(args, path, batches, last)
         extra["parity_sample"] = parity
 
@@ -386,7 +422,10 @@ def ours(args, rank, world, local_rank):
             "dtype": "f32", "data": "synthetic", "config": workload_config(world, nseg),
             "clocks": sampler.result(),
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "path": "Engine.search_batch(query strings) -> ns_engine_search_batch"},
+                    "steps": e2e_steps, "callers": callers,
+                    "single_caller_value": e2e_steps * BATCH_Q / e2e_single_s,
+                    "path": "Engine.search_batch(query strings) -> ns_engine_search_batch_packed: tokenise, "
+                            "lexicon, prepare, H2D, kernels, D2H per call; `callers` host threads issue the calls"},
             "gpu_launches": launches_per_step * K,
             "roofline": {"bound": "hbm", "achieved": ach_local, "peak": peak, "unit": "GB/s",
                          "frac": ach_local / peak, "traffic": None, "peak_source": peak_src,
@@ -449,6 +488,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--distinct-batches", type=int, default=8)
     ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--e2e-callers", type=int, default=3, help="host threads issuing e2e search_batch calls (N=1)")
     ap.add_argument("--single-queries", type=int, default=200)
     ap.add_argument("--cpu-sample", type=int, default=256)
     ap.add_argument("--profile-mode", action="store_true",

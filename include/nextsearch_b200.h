@@ -191,6 +191,12 @@ int ns_engine_search_batch(ns_engine* e, uint32_t Q, const char* const* queries,
                            ns_hit* out_hits, uint32_t* out_nhits, uint64_t* out_found,
                            uint8_t* has_found);
 
+/* Same, with the Q query strings packed back to back, each NUL-terminated, in one buffer of
+ * nbytes bytes (what a request-coalescing front end accumulates; avoids a pointer array). */
+int ns_engine_search_batch_packed(ns_engine* e, uint32_t Q, const char* zqueries, size_t nbytes, int k,
+                                  ns_hit* out_hits, uint32_t* out_nhits, uint64_t* out_found,
+                                  uint8_t* has_found);
+
 /* Front end only: tokenise + filter + lexicon lookup + IDF for a batch, producing
  * the arrays ns_search_batch takes.  Two-call protocol: pass terms=NULL to get
  * the count in *n_terms.  Only segments owned by this engine's shard are emitted. */

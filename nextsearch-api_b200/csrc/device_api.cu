@@ -96,12 +96,15 @@ struct BatchRes {
     size_t h_out_cap = 0;
     uint8_t* d_scratch = nullptr;  // per-batch impact array, grown on demand
     size_t scratch_cap = 0;
+    uint8_t* d_part = nullptr;     // per-item partial top-k lists, grown on demand
+    size_t part_cap = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     ~BatchRes() {
         cudaSetDevice(device);
         if (d_blob) cudaFree(d_blob);
         if (d_scratch) cudaFree(d_scratch);
+        if (d_part) cudaFree(d_part);
         if (h_in) cudaFreeHost(h_in);
         if (h_out) cudaFreeHost(h_out);
         for (auto& e : ev)
@@ -151,9 +154,6 @@ struct ns_batch {
     uint32_t* d_out_n = nullptr;
     unsigned long long* d_out_found = nullptr;
     size_t out_bytes = 0, off_n = 0, off_found = 0;
-    // per-item partial lists, allocated on demand
-    uint8_t* d_part = nullptr;
-    size_t d_part_cap = 0;
     bool launched = false;
 };
 
@@ -496,21 +496,25 @@ void build_items(ns_batch* b, uint32_t forced) {
         list_off[q + 1] = list_off[q] + nsplit[q];
     }
     const uint32_t nitems = list_off[Q];
-    std::vector<std::pair<uint64_t, DevItem>> items;
+    // Order: window-major (split asc), heaviest item first inside a window; query-major mode orders
+    // by item weight only.  Sorting the Q queries once replaces a sort over all Q x nsplit items.
+    std::vector<uint32_t> order(Q);
+    std::iota(order.begin(), order.end(), 0u);
+    std::vector<uint64_t> iw(Q);
+    for (uint32_t q = 0; q < Q; q++) iw[q] = b->weight[q] / nsplit[q];
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return iw[x] > iw[y]; });
+    std::vector<DevItem> items;
     items.reserve(nitems);
-    for (uint32_t q = 0; q < Q; q++)
-        for (uint32_t sp = 0; sp < nsplit[q]; sp++)
-            items.push_back({b->weight[q] / nsplit[q], DevItem{q, (sp << 16) | nsplit[q]}});
     if (window && !forced) {
-        std::stable_sort(items.begin(), items.end(), [](const auto& x, const auto& y) {
-            const uint32_t sx = x.second.split_ns >> 16, sy = y.second.split_ns >> 16;
-            return sx != sy ? sx < sy : x.first > y.first;
-        });
+        for (uint32_t sp = 0; sp < maxs; sp++)
+            for (uint32_t q : order)
+                if (sp < nsplit[q]) items.push_back(DevItem{q, (sp << 16) | nsplit[q]});
     } else {
-        std::stable_sort(items.begin(), items.end(), [](const auto& x, const auto& y) { return x.first > y.first; });
+        for (uint32_t q : order)
+            for (uint32_t sp = 0; sp < nsplit[q]; sp++) items.push_back(DevItem{q, (sp << 16) | nsplit[q]});
     }
     DevItem* h_items = reinterpret_cast<DevItem*>(b->res->h_in + b->off_items);
-    for (uint32_t i = 0; i < nitems; i++) h_items[i] = items[i].second;
+    std::memcpy(h_items, items.data(), (size_t)nitems * sizeof(DevItem));
     std::memcpy(b->res->h_in + b->off_list, list_off.data(), ((size_t)Q + 1) * 4);
     b->nitems = nitems;
     b->max_split = maxs;
@@ -713,12 +717,15 @@ static int ensure_part(ns_batch* b) {
     if (b->nitems == b->Q) return NS_OK;  // one item per query: results go straight to the output
     const size_t lists = b->nitems;
     const size_t need = align_up(lists * b->k * sizeof(ns_hit)) + align_up(lists * 4) + align_up(lists * 8);
-    if (b->d_part_cap >= need) return NS_OK;
-    if (b->d_part) cudaFree(b->d_part);
-    b->d_part = nullptr;
-    b->d_part_cap = 0;
-    NS_CUDA(cudaMalloc(&b->d_part, need));
-    b->d_part_cap = need;
+    BatchRes& r = *b->res;  // pooled with the batch's other buffers: no cudaMalloc/cudaFree per batch
+    if (r.part_cap >= need) return NS_OK;
+    if (r.d_part) cudaFree(r.d_part);
+    r.d_part = nullptr;
+    r.part_cap = 0;
+    size_t cap = 1 << 20;
+    while (cap < need) cap <<= 1;
+    NS_CUDA(cudaMalloc(&r.d_part, cap));
+    r.part_cap = cap;
     return NS_OK;
 }
 
@@ -763,9 +770,10 @@ extern "C" int ns_batch_launch(ns_batch* b, void* stream) {
         a.impacts = reinterpret_cast<const uint2*>(b->res->d_scratch);
         const size_t lists = b->nitems;
         if (split) {
-            a.hits = reinterpret_cast<ns_hit*>(b->d_part);
-            a.nhits = reinterpret_cast<uint32_t*>(b->d_part + align_up(lists * b->k * sizeof(ns_hit)));
-            a.found = reinterpret_cast<unsigned long long*>(b->d_part + align_up(lists * b->k * sizeof(ns_hit)) + align_up(lists * 4));
+            uint8_t* part = b->res->d_part;
+            a.hits = reinterpret_cast<ns_hit*>(part);
+            a.nhits = reinterpret_cast<uint32_t*>(part + align_up(lists * b->k * sizeof(ns_hit)));
+            a.found = reinterpret_cast<unsigned long long*>(part + align_up(lists * b->k * sizeof(ns_hit)) + align_up(lists * 4));
         } else {
             a.hits = b->d_out_hits;
             a.nhits = b->d_out_n;
@@ -864,7 +872,6 @@ extern "C" void ns_batch_destroy(ns_batch* b) {
     if (!b) return;
     cudaSetDevice(b->st->device);
     if (b->launched) cudaEventSynchronize(b->res->ev[2]);
-    if (b->d_part) cudaFree(b->d_part);
     if (b->owner && b->res) {
         std::lock_guard<std::mutex> lk(b->owner->mu);
         if (b->owner->pool.size() < 64) b->owner->pool.push_back(std::move(b->res));

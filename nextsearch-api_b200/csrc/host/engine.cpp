@@ -3,8 +3,11 @@
 // Tokenise / stop-filter / lexicon lookup / IDF stay on the host exactly as in the reference;
 // the per-posting work goes through ns_search_batch.
 #include <algorithm>
+#include <cstdlib>
 #include <atomic>
 #include <charconv>
+#include <chrono>
+#include <cstdio>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -18,6 +21,7 @@
 #include "corpus.hpp"
 #include "segment_io.hpp"
 #include "textutil.hpp"
+#include "workpool.hpp"
 
 using namespace nsb;
 
@@ -31,6 +35,8 @@ struct ns_engine {
     // segs[i] is loaded only when this engine owns segment i (i % world == rank)
     std::vector<std::unique_ptr<HostSegment>> segs;
     bool owns(size_t i) const { return (int)(i % (size_t)world) == rank; }
+    std::unique_ptr<WorkPool> pool;  // query front-end workers, created on first batch
+    std::once_flag pool_once;
 };
 
 namespace {
@@ -75,7 +81,7 @@ void json_double(double v, std::string& out) {
 // Resolve one query against the owned segments.  Emits terms ordered by (segment asc, query order).
 // Returns whether the reference would compute "found" (base_terms and segments non-empty).
 bool resolve_one(const ns_engine* e, const char* query, std::vector<ns_qterm>& out) {
-    std::vector<std::string> terms;
+    static thread_local std::vector<std::string> terms;
     query_terms(query, terms);
     if (terms.empty() || e->seg_names.empty()) return false;  // src/api_engine.cpp:407
     for (size_t si = 0; si < e->segs.size(); si++) {
@@ -223,59 +229,118 @@ extern "C" int ns_engine_cord_uid(const ns_engine* e, uint32_t seg, uint32_t doc
     return (int)s.size();
 }
 
+namespace {
+
+// One pass over the batch: tokenise, filter, look every term up in every owned segment's lexicon.
+// The queries are independent, so the batch is cut into contiguous ranges, one per host thread
+// (the reference serialises whole searches on Engine::mtx, src/api_engine.cpp:372).
+struct Resolved {
+    std::vector<uint64_t> q_off;   // [Q+1]
+    std::vector<ns_qterm> terms;
+    std::vector<uint8_t> has;      // [Q]
+};
+
+template <class GetQuery>
+void resolve_all(ns_engine* e, uint32_t Q, GetQuery get, Resolved& out) {
+    std::call_once(e->pool_once, [&] { e->pool.reset(new WorkPool(std::max(0, std::min(hw_threads(), 8) - 1))); });
+    static const int max_nt = std::getenv("NSB200_HOST_THREADS") ? std::atoi(std::getenv("NSB200_HOST_THREADS")) : 1 << 20;
+    const int nt = std::max(1, std::min(std::min(e->pool->workers() + 1, max_nt), (int)(Q / 256) + 1));
+    std::vector<std::vector<ns_qterm>> per((size_t)nt);
+    std::vector<uint32_t> cnt(Q, 0);
+    out.has.assign(Q, 0);
+    auto lo_of = [&](int t) { return (uint32_t)((uint64_t)Q * t / nt); };
+    auto work = [&](int t) {
+        per[t].reserve((size_t)(lo_of(t + 1) - lo_of(t)) * 4);
+        for (uint32_t q = lo_of(t); q < lo_of(t + 1); q++) {
+            const size_t before = per[t].size();
+            out.has[q] = resolve_one(e, get(q), per[t]) ? 1 : 0;
+            cnt[q] = (uint32_t)(per[t].size() - before);
+        }
+    };
+    e->pool->run(nt, work);
+    out.q_off.resize((size_t)Q + 1);
+    uint64_t total = 0;
+    out.q_off[0] = 0;
+    for (uint32_t q = 0; q < Q; q++) {
+        total += cnt[q];
+        out.q_off[q + 1] = total;
+    }
+    out.terms.resize(std::max<uint64_t>(1, total));
+    uint64_t at = 0;
+    for (int t = 0; t < nt; t++) {
+        if (!per[t].empty()) std::memcpy(out.terms.data() + at, per[t].data(), per[t].size() * sizeof(ns_qterm));
+        at += per[t].size();
+    }
+}
+
+// start of each NUL-terminated string in a packed buffer; false if fewer than Q strings fit
+bool split_packed(const char* z, size_t nbytes, uint32_t Q, std::vector<const char*>& starts) {
+    starts.resize(Q);
+    size_t at = 0;
+    for (uint32_t q = 0; q < Q; q++) {
+        if (at >= nbytes) return false;
+        starts[q] = z + at;
+        const void* nul = std::memchr(z + at, 0, nbytes - at);
+        if (!nul) return false;
+        at = (size_t)((const char*)nul - z) + 1;
+    }
+    return true;
+}
+
+}  // namespace
+
 extern "C" int ns_engine_resolve_batch(ns_engine* e, uint32_t Q, const char* const* queries, uint64_t* q_off,
                                        ns_qterm* terms, uint64_t terms_cap, uint64_t* n_terms, uint8_t* has_terms) {
     if (!e || (Q && !queries) || !q_off || !n_terms) { set_error("ns_engine_resolve_batch: null argument"); return NS_ERR_INVALID; }
     std::shared_lock<std::shared_mutex> lk(e->mu);
-    const int nt = std::max(1, std::min(hw_threads(), (int)(Q / 128) + 1));
-    std::vector<std::vector<ns_qterm>> per((size_t)nt);
-    std::vector<std::vector<uint32_t>> cnt((size_t)nt);
-    std::vector<uint8_t> has(Q, 0);
-    auto lo_of = [&](int t) { return (uint32_t)((uint64_t)Q * t / nt); };
-    auto work = [&](int t) {
-        for (uint32_t q = lo_of(t); q < lo_of(t + 1); q++) {
-            size_t before = per[t].size();
-            has[q] = resolve_one(e, queries[q], per[t]) ? 1 : 0;
-            cnt[t].push_back((uint32_t)(per[t].size() - before));
-        }
-    };
-    std::vector<std::thread> th;
-    for (int t = 1; t < nt; t++) th.emplace_back(work, t);
-    work(0);
-    for (auto& x : th) x.join();
-    uint64_t total = 0;
-    q_off[0] = 0;
-    for (int t = 0; t < nt; t++) {
-        uint32_t q = lo_of(t);
-        for (uint32_t c : cnt[t]) {
-            total += c;
-            q_off[++q] = total;
-        }
-    }
+    Resolved r;
+    resolve_all(e, Q, [&](uint32_t q) { return queries[q]; }, r);
+    const uint64_t total = r.q_off[Q];
+    std::memcpy(q_off, r.q_off.data(), ((size_t)Q + 1) * sizeof(uint64_t));
     *n_terms = total;
-    if (has_terms) std::memcpy(has_terms, has.data(), Q);
+    if (has_terms && Q) std::memcpy(has_terms, r.has.data(), Q);
     if (!terms) return NS_OK;
     if (terms_cap < total) { set_error("ns_engine_resolve_batch: terms buffer too small"); return NS_ERR_INVALID; }
-    uint64_t at = 0;
-    for (int t = 0; t < nt; t++) {
-        if (!per[t].empty()) std::memcpy(terms + at, per[t].data(), per[t].size() * sizeof(ns_qterm));
-        at += per[t].size();
-    }
+    if (total) std::memcpy(terms, r.terms.data(), total * sizeof(ns_qterm));
     return NS_OK;
 }
 
 extern "C" int ns_engine_search_batch(ns_engine* e, uint32_t Q, const char* const* queries, int k, ns_hit* out_hits,
                                       uint32_t* out_nhits, uint64_t* out_found, uint8_t* has_found) {
-    if (!e) { set_error("ns_engine_search_batch: null"); return NS_ERR_INVALID; }
+    if (!e || (Q && !queries)) { set_error("ns_engine_search_batch: null argument"); return NS_ERR_INVALID; }
     if (!e->idx) { set_error("engine was created without a CUDA device; there is no CPU search path"); return NS_ERR_STATE; }
-    std::vector<uint64_t> q_off((size_t)Q + 1);
-    uint64_t n = 0;
-    int rc = ns_engine_resolve_batch(e, Q, queries, q_off.data(), nullptr, 0, &n, has_found);
-    if (rc != NS_OK) return rc;
-    std::vector<ns_qterm> terms(std::max<uint64_t>(1, n));
-    rc = ns_engine_resolve_batch(e, Q, queries, q_off.data(), terms.data(), terms.size(), &n, has_found);
-    if (rc != NS_OK) return rc;
-    return ns_search_batch(e->idx, Q, k, q_off.data(), terms.data(), out_hits, out_nhits, out_found);
+    Resolved r;
+    {
+        std::shared_lock<std::shared_mutex> lk(e->mu);
+        resolve_all(e, Q, [&](uint32_t q) { return queries[q]; }, r);
+    }
+    if (has_found && Q) std::memcpy(has_found, r.has.data(), Q);
+    return ns_search_batch(e->idx, Q, k, r.q_off.data(), r.terms.data(), out_hits, out_nhits, out_found);
+}
+
+extern "C" int ns_engine_search_batch_packed(ns_engine* e, uint32_t Q, const char* zqueries, size_t nbytes, int k,
+                                             ns_hit* out_hits, uint32_t* out_nhits, uint64_t* out_found,
+                                             uint8_t* has_found) {
+    if (!e || (Q && !zqueries)) { set_error("ns_engine_search_batch_packed: null argument"); return NS_ERR_INVALID; }
+    if (!e->idx) { set_error("engine was created without a CUDA device; there is no CPU search path"); return NS_ERR_STATE; }
+    std::vector<const char*> starts;
+    if (!split_packed(zqueries, nbytes, Q, starts)) {
+        set_error("ns_engine_search_batch_packed: buffer holds fewer than Q NUL-terminated strings");
+        return NS_ERR_INVALID;
+    }
+    Resolved r;
+    static const bool trace = std::getenv("NSB200_TRACE") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
+    {
+        std::shared_lock<std::shared_mutex> lk(e->mu);
+        resolve_all(e, Q, [&](uint32_t q) { return starts[q]; }, r);
+    }
+    if (trace)
+        std::fprintf(stderr, "[nsb200] Q=%u resolve %.3f ms (%llu terms)\n", Q,
+                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(),
+                     (unsigned long long)r.q_off[Q]);
+    if (has_found && Q) std::memcpy(has_found, r.has.data(), Q);
+    return ns_search_batch(e->idx, Q, k, r.q_off.data(), r.terms.data(), out_hits, out_nhits, out_found);
 }
 
 extern "C" int ns_engine_search_json(ns_engine* e, const char* query, int k, char* buf, size_t cap, size_t* needed) {

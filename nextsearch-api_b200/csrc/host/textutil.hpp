@@ -37,7 +37,7 @@ inline bool is_stopword(const std::string& t) {
 }
 
 inline void query_terms(const char* query, std::vector<std::string>& out) {
-    std::vector<std::string> toks;
+    static thread_local std::vector<std::string> toks;  // reused: no allocation per query in steady state
     tokenize(query, toks);
     out.clear();
     for (auto& t : toks) {

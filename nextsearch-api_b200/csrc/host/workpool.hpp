@@ -1,0 +1,89 @@
+// Persistent host worker pool for the query front end: spawning std::threads per batch costs
+// ~0.5 ms, a good part of a 2 ms batch.  run(n, fn) executes fn(0..n-1), the caller taking part,
+// and returns when all are done.  One run at a time per pool (callers serialise on run_mu).
+#pragma once
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+namespace nsb {
+
+class WorkPool {
+  public:
+    explicit WorkPool(int workers) {
+        for (int i = 0; i < workers; i++) th_.emplace_back([this] { loop(); });
+    }
+    ~WorkPool() {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto& t : th_) t.join();
+    }
+    int workers() const { return (int)th_.size(); }
+
+    void run(int n, const std::function<void(int)>& fn) {
+        if (n <= 0) return;
+        if (n == 1 || th_.empty()) {
+            for (int i = 0; i < n; i++) fn(i);
+            return;
+        }
+        std::lock_guard<std::mutex> one(run_mu_);
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            fn_ = &fn;
+            n_ = n;
+            next_.store(0, std::memory_order_relaxed);
+            done_ = 0;
+            gen_++;
+        }
+        cv_.notify_all();
+        drain();
+        std::unique_lock<std::mutex> lk(mu_);
+        done_cv_.wait(lk, [&] { return done_ == n_.load(); });
+        fn_ = nullptr;
+    }
+
+  private:
+    void drain() {
+        int mine = 0;
+        for (;;) {
+            const int i = next_.fetch_add(1, std::memory_order_relaxed);
+            if (i >= n_) break;
+            (*fn_)(i);
+            mine++;
+        }
+        if (mine) {
+            std::lock_guard<std::mutex> lk(mu_);
+            done_ += mine;
+            if (done_ == n_) done_cv_.notify_all();
+        }
+    }
+    void loop() {
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return stop_ || gen_ != seen; });
+                if (stop_) return;
+                seen = gen_;
+            }
+            drain();
+        }
+    }
+    std::vector<std::thread> th_;
+    std::mutex mu_, run_mu_;
+    std::condition_variable cv_, done_cv_;
+    const std::function<void(int)>* fn_ = nullptr;
+    std::atomic<int> next_{0};
+    std::atomic<int> n_{0};
+    int done_ = 0;
+    uint64_t gen_ = 0;
+    bool stop_ = false;
+};
+
+}  // namespace nsb

@@ -297,12 +297,18 @@ class Engine:
         """Q query strings through tokenizer, lexicon, H2D, kernels, D2H — the e2e call."""
         Q = len(queries)
         K = clamp_k(k)
-        arr = _cstr_array(queries)
-        hits = np.zeros((Q, K), dtype=HIT_DTYPE)
-        nhits = np.zeros(Q, dtype=np.uint32)
-        found = np.zeros(Q, dtype=np.uint64)
+        hits = np.empty((Q, K), dtype=HIT_DTYPE)
+        nhits = np.empty(Q, dtype=np.uint32)
+        found = np.empty(Q, dtype=np.uint64)
         has = np.zeros(max(1, Q), dtype=np.uint8)
-        check(self._lib.ns_engine_search_batch(self._h, Q, arr, int(k), _ptr(hits), _ptr(nhits), _ptr(found), _ptr(has)))
+        if any("\0" in q for q in queries):  # C strings end at NUL: keep that behaviour
+            arr = _cstr_array(queries)
+            check(self._lib.ns_engine_search_batch(self._h, Q, arr, int(k), _ptr(hits), _ptr(nhits), _ptr(found),
+                                                   _ptr(has)))
+        else:
+            z = ("\0".join(queries) + "\0").encode("utf-8") if Q else b""
+            check(self._lib.ns_engine_search_batch_packed(self._h, Q, z, len(z), int(k), _ptr(hits), _ptr(nhits),
+                                                          _ptr(found), _ptr(has)))
         return BatchResult(hits, nhits, found, has[:Q].astype(bool), K)
 
     def close(self) -> None:
