@@ -523,6 +523,7 @@ void build_items(ns_batch* b, uint32_t forced) {
 struct KernelCfg {
     const void* fn;
     size_t smem;
+    int threads = kThreads;
 };
 
 template <int TDW, int KCAP, bool FAST, bool IMPACT, int NG>
@@ -782,6 +783,7 @@ extern "C" int ns_batch_launch(ns_batch* b, void* stream) {
         static const bool no_fast = std::getenv("NSB200_NO_FAST") != nullptr;
         const bool fast = b->fast && !no_fast;
         const KernelCfg cfg = pick_kernel(b->k, fast, b->impact, b->max_in_seg > 32u);
+        const uint32_t warps_per_block = (uint32_t)cfg.threads / 32u;
         // the smem opt-in and the occupancy query cost ~0.4 ms of host time per call: once per
         // (device, kernel variant)
         int per_sm = 0;
@@ -790,7 +792,7 @@ extern "C" int ns_batch_launch(ns_batch* b, void* stream) {
             auto it = b->owner->occupancy.find(cfg.fn);
             if (it == b->owner->occupancy.end()) {
                 NS_CUDA(cudaFuncSetAttribute(cfg.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
-                NS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cfg.fn, kThreads, cfg.smem));
+                NS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cfg.fn, cfg.threads, cfg.smem));
                 b->owner->occupancy[cfg.fn] = per_sm;
             } else {
                 per_sm = it->second;
@@ -798,7 +800,7 @@ extern "C" int ns_batch_launch(ns_batch* b, void* stream) {
         }
         if (per_sm < 1) { set_error("score kernel does not fit on an SM"); return NS_ERR_CUDA; }
         uint32_t grid = (uint32_t)b->owner->sm_count * (uint32_t)per_sm;
-        grid = std::min<uint32_t>(grid, (b->nitems + kWarpsPerBlock - 1) / kWarpsPerBlock);
+        grid = std::min<uint32_t>(grid, (b->nitems + warps_per_block - 1) / warps_per_block);
         grid = std::max<uint32_t>(grid, 1);
         if (b->impact && b->ndist > 0) {
             ImpactArgs ia;
@@ -816,7 +818,7 @@ extern "C" int ns_batch_launch(ns_batch* b, void* stream) {
             NS_CUDA(cudaGetLastError());
         }
         void* kargs[] = {(void*)&a};
-        NS_CUDA(cudaLaunchKernel(cfg.fn, dim3(grid), dim3(kThreads), kargs, cfg.smem, s));
+        NS_CUDA(cudaLaunchKernel(cfg.fn, dim3(grid), dim3(cfg.threads), kargs, cfg.smem, s));
         NS_CUDA(cudaEventRecord(b->res->ev[1], s));
         if (split) {
             MergeArgs m;
