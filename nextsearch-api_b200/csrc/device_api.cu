@@ -96,15 +96,12 @@ struct BatchRes {
     size_t h_out_cap = 0;
     uint8_t* d_scratch = nullptr;  // per-batch impact array, grown on demand
     size_t scratch_cap = 0;
-    uint8_t* d_part = nullptr;     // per-item partial top-k lists, grown on demand
-    size_t part_cap = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     ~BatchRes() {
         cudaSetDevice(device);
         if (d_blob) cudaFree(d_blob);
         if (d_scratch) cudaFree(d_scratch);
-        if (d_part) cudaFree(d_part);
         if (h_in) cudaFreeHost(h_in);
         if (h_out) cudaFreeHost(h_out);
         for (auto& e : ev)
@@ -203,6 +200,7 @@ extern "C" int ns_index_add_segment(ns_index* idx, uint32_t global_seg, uint32_t
         return NS_ERR_INVALID;
     }
     if (P >= 0xFFFFFFFFull) { set_error("segment has >= 2^32 postings; split it"); return NS_ERR_INVALID; }
+    if (global_seg >= 0x80000000u) { set_error("ns_index_add_segment: global_seg must be < 2^31"); return NS_ERR_INVALID; }
     std::vector<uint32_t> begin32(T);
     for (uint32_t t = 0; t < T; t++) {
         if (term_begin[t] + term_count[t] > P) {
@@ -714,22 +712,6 @@ extern "C" int ns_batch_prepare(ns_index* idx, uint32_t Q, int k_in, const uint6
     return NS_OK;
 }
 
-static int ensure_part(ns_batch* b) {
-    if (b->nitems == b->Q) return NS_OK;  // one item per query: results go straight to the output
-    const size_t lists = b->nitems;
-    const size_t need = align_up(lists * b->k * sizeof(ns_hit)) + align_up(lists * 4) + align_up(lists * 8);
-    BatchRes& r = *b->res;  // pooled with the batch's other buffers: no cudaMalloc/cudaFree per batch
-    if (r.part_cap >= need) return NS_OK;
-    if (r.d_part) cudaFree(r.d_part);
-    r.d_part = nullptr;
-    r.part_cap = 0;
-    size_t cap = 1 << 20;
-    while (cap < need) cap <<= 1;
-    NS_CUDA(cudaMalloc(&r.d_part, cap));
-    r.part_cap = cap;
-    return NS_OK;
-}
-
 extern "C" int ns_batch_set_splits(ns_batch* b, uint32_t splits) {
     if (!b) return NS_ERR_INVALID;
     NS_CUDA(cudaSetDevice(b->st->device));
@@ -746,12 +728,11 @@ extern "C" int ns_batch_launch(ns_batch* b, void* stream) {
     if (!b) { set_error("ns_batch_launch: null"); return NS_ERR_INVALID; }
     NS_CUDA(cudaSetDevice(b->st->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : b->res->stream;
-    int rc = ensure_part(b);
-    if (rc != NS_OK) return rc;
-    const bool split = b->nitems != b->Q;
     NS_CUDA(cudaEventRecord(b->res->ev[0], s));
     if (b->Q > 0) {
+        // work-queue head + per-query locks, and the shared result lists the items merge into
         NS_CUDA(cudaMemsetAsync(b->d_counter, 0, 4 + (size_t)b->Q * 4, s));
+        NS_CUDA(cudaMemsetAsync(b->d_out, 0, b->out_bytes, s));
         ScoreArgs a;
         a.segs = b->st->d_segs;
         a.tile_base = b->st->d_tile_base;
@@ -760,26 +741,17 @@ extern "C" int ns_batch_launch(ns_batch* b, void* stream) {
         a.qoff = b->d_qoff;
         a.terms = b->d_terms;
         a.items = b->d_items;
-        a.list_off = b->d_list_off;
         a.counter = b->d_counter;
-        a.qthr = b->d_counter + 1;
+        a.qlock = b->d_counter + 1;
         a.nitems = b->nitems;
         a.k = b->k;
         a.scan_always = b->scan_always ? 1u : 0u;
         a.k1p1 = kK1 + 1.0f;
         a.zero = 0u;
         a.impacts = reinterpret_cast<const uint2*>(b->res->d_scratch);
-        const size_t lists = b->nitems;
-        if (split) {
-            uint8_t* part = b->res->d_part;
-            a.hits = reinterpret_cast<ns_hit*>(part);
-            a.nhits = reinterpret_cast<uint32_t*>(part + align_up(lists * b->k * sizeof(ns_hit)));
-            a.found = reinterpret_cast<unsigned long long*>(part + align_up(lists * b->k * sizeof(ns_hit)) + align_up(lists * 4));
-        } else {
-            a.hits = b->d_out_hits;
-            a.nhits = b->d_out_n;
-            a.found = b->d_out_found;
-        }
+        a.hits = b->d_out_hits;
+        a.nhits = b->d_out_n;
+        a.found = b->d_out_found;
         static const bool no_fast = std::getenv("NSB200_NO_FAST") != nullptr;
         const bool fast = b->fast && !no_fast;
         const KernelCfg cfg = pick_kernel(b->k, fast, b->impact, b->max_in_seg > 32u);
@@ -820,27 +792,6 @@ extern "C" int ns_batch_launch(ns_batch* b, void* stream) {
         void* kargs[] = {(void*)&a};
         NS_CUDA(cudaLaunchKernel(cfg.fn, dim3(grid), dim3(cfg.threads), kargs, cfg.smem, s));
         NS_CUDA(cudaEventRecord(b->res->ev[1], s));
-        if (split) {
-            MergeArgs m;
-            m.hits = reinterpret_cast<const unsigned char*>(a.hits);
-            m.nhits = reinterpret_cast<const unsigned char*>(a.nhits);
-            m.found = reinterpret_cast<const unsigned char*>(a.found);
-            m.hits_lsb = (uint64_t)b->k * sizeof(ns_hit);
-            m.n_lsb = 4;
-            m.f_lsb = 8;
-            m.qs = 0;
-            m.qs2 = 0;
-            m.list_off = b->d_list_off;
-            m.Q = b->Q;
-            m.k = b->k;
-            m.nlists = b->max_split;
-            m.out_hits = b->d_out_hits;
-            m.out_nhits = b->d_out_n;
-            m.out_found = b->d_out_found;
-            const size_t smem = (size_t)kMergeWarps * b->max_split * sizeof(unsigned short);
-            topk_merge_kernel<<<(b->Q + kMergeWarps - 1) / kMergeWarps, kMergeWarps * 32, smem, s>>>(m);
-            NS_CUDA(cudaGetLastError());
-        }
     } else {
         NS_CUDA(cudaEventRecord(b->res->ev[1], s));
     }
@@ -892,7 +843,7 @@ extern "C" int ns_batch_device_results(ns_batch* b, void** d_hits, void** d_nhit
 extern "C" uint64_t ns_batch_posting_count(const ns_batch* b) { return b ? b->postings : 0; }
 extern "C" uint32_t ns_batch_num_launches(const ns_batch* b) {
     if (!b || b->Q == 0) return 0u;
-    return 1u + (b->impact && b->ndist > 0 ? 1u : 0u) + (b->nitems != b->Q ? 1u : 0u);
+    return 1u + (b->impact && b->ndist > 0 ? 1u : 0u);
 }
 
 extern "C" float ns_batch_last_kernel_ms(ns_batch* b, int which) {
