@@ -414,6 +414,9 @@ def ours(args, rank, world, local_rank):
         extra["p50_ms_batch_e2e"] = 1e3 * e2e_single_s / e2e_steps
         cpu_baseline, parity = cpu_baseline_leg(args, path, batches, last)
         extra["parity_sample"] = parity
+    elif rank == 0:
+        # sharded run: the merged answer of the last e2e batch against the oracle on the same 8-segment index
+        extra["parity_sample"] = parity_check(path, batches, last, (e2e_steps - 1) % nb)
 
     if rank == 0:
         line = {
@@ -441,6 +444,32 @@ def ours(args, rank, world, local_rank):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def parity_check(path, batches, last_result, b_idx, nchk=256):
+    import numpy as np
+
+    from oracle import oracle as orc
+
+    oi = orc.OracleIndex(path)
+    nchk = min(nchk, len(batches[b_idx]))
+    qs = batches[b_idx][:nchk]
+    _, s, g, d, nh, fo, hf = oi.search_many(qs, TOPK, nthreads=os.cpu_count() or 1)
+    ok = bool(np.array_equal(last_result.nhits[:nchk], nh) and np.array_equal(last_result.found[:nchk], fo))
+    if not ok:
+        bad = [q for q in range(nchk) if last_result.nhits[q] != nh[q] or last_result.found[q] != fo[q]][:3]
+        log(f"[bench] parity: nhits/found differ at {bad}: got {[(int(last_result.nhits[q]), int(last_result.found[q])) for q in bad]} "
+            f"want {[(int(nh[q]), int(fo[q])) for q in bad]} queries {[qs[q] for q in bad]}")
+    for q in range(nchk):
+        n = int(nh[q])
+        same = (np.array_equal(last_result.hits["score"][q, :n].view(np.uint32), s[q, :n].view(np.uint32))
+                and np.array_equal(last_result.hits["doc"][q, :n], d[q, :n])
+                and np.array_equal(last_result.hits["seg"][q, :n], g[q, :n]))
+        if not same and ok:
+            log(f"[bench] parity: query {q} {qs[q]!r}: got {last_result.hits[q, :n].tolist()} want "
+                f"{list(zip(s[q, :n].tolist(), g[q, :n].tolist(), d[q, :n].tolist()))}")
+        ok = ok and same
+    return {"queries": nchk, "bit_exact_vs_oracle": bool(ok)}
 
 
 def cpu_baseline_leg(args, path, batches, last_result):

@@ -203,6 +203,10 @@ int ns_engine_search_batch_packed(ns_engine* e, uint32_t Q, const char* zqueries
 int ns_engine_resolve_batch(ns_engine* e, uint32_t Q, const char* const* queries,
                             uint64_t* q_off, ns_qterm* terms, uint64_t terms_cap, uint64_t* n_terms,
                             uint8_t* has_terms);
+/* Same with the query strings packed back to back (each NUL-terminated) in one buffer. */
+int ns_engine_resolve_batch_packed(ns_engine* e, uint32_t Q, const char* zqueries, size_t nbytes,
+                                   uint64_t* q_off, ns_qterm* terms, uint64_t terms_cap, uint64_t* n_terms,
+                                   uint8_t* has_terms);
 ns_index* ns_engine_index(ns_engine* e);
 /* cord_uid of (segment, doc); returns length or -1 */
 int ns_engine_cord_uid(const ns_engine* e, uint32_t seg, uint32_t doc, char* buf, size_t cap);

@@ -80,6 +80,7 @@ SYMBOLS = {
     "ns_engine_term_stats": (C.c_int, [_P, C.c_int, C.c_char_p, _u32p, _u32p]),
     "ns_engine_search_json": (C.c_int, [_P, C.c_char_p, C.c_int, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "ns_engine_search_batch": (C.c_int, [_P, C.c_uint32, _strs, C.c_int, _P, _P, _P, _P]),
+    "ns_engine_resolve_batch_packed": (C.c_int, [_P, C.c_uint32, C.c_char_p, C.c_size_t, _P, _P, C.c_uint64, _u64p, _P]),
     "ns_engine_search_batch_packed": (C.c_int, [_P, C.c_uint32, C.c_char_p, C.c_size_t, C.c_int, _P, _P, _P, _P]),
     "ns_engine_resolve_batch": (C.c_int, [_P, C.c_uint32, _strs, _P, _P, C.c_uint64, _u64p, _P]),
     "ns_engine_index": (_P, [_P]),

@@ -305,6 +305,28 @@ extern "C" int ns_engine_resolve_batch(ns_engine* e, uint32_t Q, const char* con
     return NS_OK;
 }
 
+extern "C" int ns_engine_resolve_batch_packed(ns_engine* e, uint32_t Q, const char* zqueries, size_t nbytes,
+                                              uint64_t* q_off, ns_qterm* terms, uint64_t terms_cap, uint64_t* n_terms,
+                                              uint8_t* has_terms) {
+    if (!e || (Q && !zqueries) || !q_off || !n_terms) { set_error("ns_engine_resolve_batch_packed: null argument"); return NS_ERR_INVALID; }
+    std::vector<const char*> starts;
+    if (!split_packed(zqueries, nbytes, Q, starts)) {
+        set_error("ns_engine_resolve_batch_packed: buffer holds fewer than Q NUL-terminated strings");
+        return NS_ERR_INVALID;
+    }
+    std::shared_lock<std::shared_mutex> lk(e->mu);
+    Resolved r;
+    resolve_all(e, Q, [&](uint32_t q) { return starts[q]; }, r);
+    const uint64_t total = r.q_off[Q];
+    std::memcpy(q_off, r.q_off.data(), ((size_t)Q + 1) * sizeof(uint64_t));
+    *n_terms = total;
+    if (has_terms && Q) std::memcpy(has_terms, r.has.data(), Q);
+    if (!terms) return NS_OK;
+    if (terms_cap < total) { set_error("ns_engine_resolve_batch_packed: terms buffer too small"); return NS_ERR_INVALID; }
+    if (total) std::memcpy(terms, r.terms.data(), total * sizeof(ns_qterm));
+    return NS_OK;
+}
+
 extern "C" int ns_engine_search_batch(ns_engine* e, uint32_t Q, const char* const* queries, int k, ns_hit* out_hits,
                                       uint32_t* out_nhits, uint64_t* out_found, uint8_t* has_found) {
     if (!e || (Q && !queries)) { set_error("ns_engine_search_batch: null argument"); return NS_ERR_INVALID; }

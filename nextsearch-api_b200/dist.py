@@ -73,9 +73,7 @@ class ShardedBatch:
     k: int
     local_blob: "object"      # torch uint8 view of the batch's device result blob
     gathered: "object"        # torch uint8 [world * blob_bytes]
-    out_hits: "object"        # torch uint8 [Q*k*12]
-    out_nhits: "object"       # torch int32 [Q]
-    out_found: "object"       # torch int64 [Q]
+    out: "object"             # torch uint8 [blob_bytes]: merged hits | nhits | found (same layout as a rank blob)
     blob_bytes: int
     off_n: int
     off_f: int
@@ -106,15 +104,16 @@ class ShardedSearcher:
         return ShardedBatch(
             batch=b, has_found=has, Q=Q, k=K, local_blob=local,
             gathered=torch.empty(self.world * nbytes.value, dtype=torch.uint8, device=dev),
-            out_hits=torch.empty(max(1, Q * K) * HIT_DTYPE.itemsize, dtype=torch.uint8, device=dev),
-            out_nhits=torch.empty(max(1, Q), dtype=torch.int32, device=dev),
-            out_found=torch.empty(max(1, Q), dtype=torch.int64, device=dev),
+            out=torch.empty(nbytes.value, dtype=torch.uint8, device=dev),
             blob_bytes=nbytes.value, off_n=off_n.value, off_f=off_f.value)
 
     def launch(self, sb: ShardedBatch) -> None:
         """score+top-k on this rank's segments -> all-gather -> merge, all on torch's current stream."""
         torch, dist = self.torch, self.dist
-        stream = torch.cuda.current_stream(self.device).cuda_stream
+        # torch's default stream has handle 0, which ns_batch_launch reads as "the batch's own stream";
+        # name it explicitly (cudaStreamLegacy == 0x1) so that the kernels, the all-gather and the merge
+        # are ordered on ONE stream — otherwise NCCL may read the local blob while it is still written
+        stream = torch.cuda.current_stream(self.device).cuda_stream or 1
         sb.batch.launch(stream)
         if self.world > 1:
             dist.all_gather_into_tensor(sb.gathered, sb.local_blob, group=self.group)
@@ -122,15 +121,14 @@ class ShardedSearcher:
         else:
             src = sb.local_blob
         lib = _lib.load()
+        base = sb.out.data_ptr()
         check(lib.ns_merge_blobs_device(self.device, sb.Q, sb.k, self.world, C.c_void_p(src.data_ptr()),
-                                        sb.blob_bytes, sb.off_n, sb.off_f, C.c_void_p(sb.out_hits.data_ptr()),
-                                        C.c_void_p(sb.out_nhits.data_ptr()), C.c_void_p(sb.out_found.data_ptr()),
+                                        sb.blob_bytes, sb.off_n, sb.off_f, C.c_void_p(base),
+                                        C.c_void_p(base + sb.off_n), C.c_void_p(base + sb.off_f),
                                         C.c_void_p(stream) if stream else None))
 
     def fetch(self, sb: ShardedBatch) -> BatchResult:
-        hits = sb.out_hits.cpu().numpy()[: sb.Q * sb.k * HIT_DTYPE.itemsize].view(HIT_DTYPE).reshape(sb.Q, sb.k)
-        nhits = sb.out_nhits.cpu().numpy()[: sb.Q].view(np.uint32)
-        found = sb.out_found.cpu().numpy()[: sb.Q].view(np.uint64)
+        hits, nhits, found = unpack_blob(sb.out.cpu().numpy(), sb.Q, sb.k)  # one D2H copy
         return BatchResult(hits, nhits, found, sb.has_found, sb.k)
 
     def search_batch(self, queries: Sequence[str], k: int = 10) -> BatchResult:

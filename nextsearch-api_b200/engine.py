@@ -283,14 +283,31 @@ class Engine:
     def resolve_batch(self, queries: Sequence[str]) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
         """Host front end only: (q_off[Q+1] u64, terms QTERM_DTYPE, has_terms[Q] bool)."""
         Q = len(queries)
-        arr = _cstr_array(queries)
         q_off = np.zeros(Q + 1, dtype=np.uint64)
         has = np.zeros(max(1, Q), dtype=np.uint8)
         n = C.c_uint64()
-        check(self._lib.ns_engine_resolve_batch(self._h, Q, arr, _ptr(q_off), None, 0, C.byref(n), _ptr(has)))
-        terms = np.zeros(max(1, n.value), dtype=QTERM_DTYPE)
-        check(self._lib.ns_engine_resolve_batch(self._h, Q, arr, _ptr(q_off), _ptr(terms), len(terms), C.byref(n),
-                                                _ptr(has)))
+        packed = not any("\0" in q for q in queries)
+        if packed:
+            z = ("\0".join(queries) + "\0").encode("utf-8") if Q else b""
+
+            def call(terms, cap):
+                return self._lib.ns_engine_resolve_batch_packed(self._h, Q, z, len(z), _ptr(q_off), terms, cap, C.byref(n),
+                                                                _ptr(has))
+        else:
+            arr = _cstr_array(queries)
+
+            def call(terms, cap):
+                return self._lib.ns_engine_resolve_batch(self._h, Q, arr, _ptr(q_off), terms, cap, C.byref(n), _ptr(has))
+
+        # one pass with a generous buffer; the exact count comes back in n if it was too small
+        cap = max(64, 8 * Q * max(1, self.num_segments // max(1, self.world) + 1))
+        terms = np.empty(cap, dtype=QTERM_DTYPE)
+        rc = call(_ptr(terms), cap)
+        if rc != _lib.NS_OK and n.value > cap:
+            cap = n.value
+            terms = np.empty(cap, dtype=QTERM_DTYPE)
+            rc = call(_ptr(terms), cap)
+        check(rc)
         return q_off, terms[: n.value], has[:Q].astype(bool)
 
     def search_batch(self, queries: Sequence[str], k: int = 10) -> BatchResult:

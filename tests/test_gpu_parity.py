@@ -298,3 +298,79 @@ def test_foreign_idf_mixes_resident_and_per_batch_scores(small_case, small_engin
             assert np.array_equal(h0["score"][q, :n].view(np.uint32), h1["score"][q, :n].view(np.uint32)), qs[q]
             assert np.array_equal(h0["doc"][q, :n], h1["doc"][q, :n]) and np.array_equal(h0["seg"][q, :n], h1["seg"][q, :n])
     plain.close()
+
+
+def test_sharded_blobs_merge_on_device(workdir):
+    """BASELINE configs[2] in small: 8 segments, two shard engines (segment i -> shard i % 2) on the
+    same GPU, their result blobs laid out back to back like the all-gather output, merged by
+    ns_merge_blobs_device — must equal the oracle on the full 8-segment index."""
+    import ctypes as C
+    torch = pytest.importorskip("torch")
+    from nextsearch_api_b200 import dist as nsdist
+
+    spec = nsb200.CorpusSpec(vocab=4000)
+    case = make_case(workdir, "eightseg", spec, 8000, 8)
+    qs = nsb200.make_queries(spec, 300, 1, 5) + EDGE_QUERIES
+    lib = nsb200._lib.load()
+    for k in (10, 100):
+        engines = [nsb200.Engine(case.path, device=0, rank=r, world=2) for r in range(2)]
+        blobs, has = [], None
+        K = nsb200.clamp_k(k)
+        total, off_n, off_f = nsdist.blob_layout(len(qs), K)
+        gathered = torch.zeros(2 * total, dtype=torch.uint8, device="cuda:0")
+        batches = []
+        for r, e in enumerate(engines):
+            assert e.reload(), e.last_error
+            q_off, terms, has = e.resolve_batch(qs)
+            assert set(np.unique(terms["seg"]).tolist()) <= {s for s in range(8) if s % 2 == r}
+            b = e.index.prepare(q_off, terms, k)
+            b.launch()
+            b.sync()
+            ptr, nbytes, o_n, o_f = C.c_void_p(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+            nsb200._lib.check(lib.ns_batch_result_blob(b._h, C.byref(ptr), C.byref(nbytes), C.byref(o_n), C.byref(o_f)))
+            assert (nbytes.value, o_n.value, o_f.value) == (total, off_n, off_f)
+            local = torch.as_tensor(nsdist._DevMem(ptr.value, nbytes.value), device="cuda:0")
+            gathered[r * total:(r + 1) * total].copy_(local)
+            batches.append(b)
+        out_hits = torch.zeros(len(qs) * K * 12, dtype=torch.uint8, device="cuda:0")
+        out_n = torch.zeros(len(qs), dtype=torch.int32, device="cuda:0")
+        out_f = torch.zeros(len(qs), dtype=torch.int64, device="cuda:0")
+        torch.cuda.synchronize()
+        nsb200._lib.check(lib.ns_merge_blobs_device(0, len(qs), k, 2, C.c_void_p(gathered.data_ptr()), total, off_n, off_f,
+                                                    C.c_void_p(out_hits.data_ptr()), C.c_void_p(out_n.data_ptr()),
+                                                    C.c_void_p(out_f.data_ptr()), None))
+        torch.cuda.synchronize()
+        res = nsb200.BatchResult(out_hits.cpu().numpy().view(nsb200.HIT_DTYPE).reshape(len(qs), K),
+                                 out_n.cpu().numpy().view(np.uint32), out_f.cpu().numpy().view(np.uint64), has, K)
+        assert_same_as_oracle(res, case.oracle, qs, k)
+        for b in batches:
+            b.close()
+        for e in engines:
+            e.close()
+
+
+def test_high_df_top100(workdir):
+    """BASELINE configs[3]: every query contains a very frequent term (df > 10 % of the corpus), k=100."""
+    spec = nsb200.CorpusSpec(vocab=20_000)
+    case = make_case(workdir, "highdf", spec, 30_000, 2)
+    e = nsb200.Engine(case.path, device=0)
+    assert e.reload(), e.last_error
+    qs = nsb200.make_queries(spec, 200, 1, 5, seed=11, head_ranks=40)
+    df, _ = e.term_stats(0, qs[0].split()[0])
+    assert df > 0.10 * case.oracle.segment_stats(0)["N"]
+    assert_same_as_oracle(e.search_batch(qs, 100), case.oracle, qs, 100)
+    assert_same_as_oracle(e.search_batch(qs, 10), case.oracle, qs, 10)
+    e.close()
+
+
+def test_long_slices_200k_docs(workdir):
+    """A corpus large enough that frequent terms have several full 128-posting groups per 2048-doc
+    tile (the double-buffered path) and that items span many tiles and segment boundaries."""
+    spec = nsb200.CorpusSpec(vocab=60_000)
+    case = make_case(workdir, "mid200k", spec, 200_000, 3)
+    e = nsb200.Engine(case.path, device=0)
+    assert e.reload(), e.last_error
+    qs = nsb200.make_queries(spec, 384, 1, 5, seed=5) + nsb200.make_queries(spec, 128, 2, 5, seed=6, head_ranks=30)
+    assert_same_as_oracle(e.search_batch(qs, 10), case.oracle, qs, 10)
+    assert_same_as_oracle(e.search_batch(qs[:128], 100), case.oracle, qs[:128], 100)
+    e.close()
