@@ -16,6 +16,7 @@
 
 #include "../../include/nextsearch_b200.h"
 #include "bm25_kernels.cuh"
+#include "bm25_stream.cuh"
 #include "host/common.hpp"
 #include "host/segment_io.hpp"
 
@@ -129,6 +130,7 @@ struct ns_batch {
     std::unique_ptr<BatchRes> res;
     uint32_t Q = 0, k = 0;
     uint32_t nitems = 0, max_split = 1;
+    bool window_major = false;  // items ordered by doc window first (build_items)
     bool scan_always = false;
     bool fast = false;  // operand ranges validated + unit weights: FAST kernel variant
     bool impact = false;           // per-batch shared term scores (impact pre-pass)
@@ -481,6 +483,18 @@ void build_items(ns_batch* b, uint32_t forced) {
     // items are ordered by window first, so that all resident warps sweep the same doc range of
     // the index at the same time and the hot posting slices are served from L2.
     uint32_t window = 16;  // measured best on 1M docs x 4096 queries (profiles/r1_v4_summary.md); 0 = query-major
+    // Items per query: ~10 items per resident warp over the whole batch, at least tiles/16 (windows of
+    // <= 16 tiles keep the batch's hot slices in L2), at most tiles/4 — and at most 16 for small batches,
+    // where all items of a query run at the same time and serialise on the query's result-list lock.
+    {
+        const uint64_t warps = (uint64_t)b->owner->sm_count * 24;
+        uint64_t ns = warps * 10 / std::max<uint32_t>(1, Q);
+        ns = std::max<uint64_t>(ns, (tiles + 15) / 16);
+        ns = std::min<uint64_t>(ns, std::max<uint32_t>(1, tiles / 4));
+        if (Q < 256) ns = std::min<uint64_t>(ns, 16);
+        ns = std::max<uint64_t>(1, ns);
+        window = (uint32_t)((tiles + ns - 1) / ns);
+    }
     if (const char* s = std::getenv("NSB200_WINDOW_TILES")) window = (uint32_t)std::max(0, std::atoi(s));
     std::vector<uint32_t> nsplit(Q);
     std::vector<uint32_t> list_off((size_t)Q + 1, 0);
@@ -503,6 +517,7 @@ void build_items(ns_batch* b, uint32_t forced) {
     std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return iw[x] > iw[y]; });
     std::vector<DevItem> items;
     items.reserve(nitems);
+    b->window_major = window && !forced;
     if (window && !forced) {
         for (uint32_t sp = 0; sp < maxs; sp++)
             for (uint32_t q : order)
@@ -524,9 +539,24 @@ struct KernelCfg {
     int threads = kThreads;
 };
 
+// NSB200_KERNEL=stream selects the chunk-stream kernel (bm25_stream.cuh); default is the slice-nest kernel.
+bool use_nest_kernel() {
+    static const bool nest = [] {
+        const char* s = std::getenv("NSB200_KERNEL");
+        return !(s && std::strcmp(s, "stream") == 0);
+    }();
+    return nest;
+}
+
 template <int TDW, int KCAP, bool FAST, bool IMPACT, int NG>
 KernelCfg cfg_of() {
-    return KernelCfg{(const void*)bm25_score_topk_kernel<TDW, KCAP, FAST, IMPACT, NG>,
+    if (use_nest_kernel())
+        return KernelCfg{(const void*)bm25_score_topk_kernel<TDW, KCAP, FAST, IMPACT, NG>,
+                         sizeof(WarpSmem<TDW, KCAP>) * kWarpsPerBlock};
+    if (NG > 1)  // more than 32 terms for one (query, segment): the nest kernel's two register groups
+        return KernelCfg{(const void*)bm25_score_topk_kernel<TDW, KCAP, FAST, IMPACT, NG>,
+                         sizeof(WarpSmem<TDW, KCAP>) * kWarpsPerBlock};
+    return KernelCfg{(const void*)bm25_stream_kernel<TDW, KCAP, FAST, IMPACT>,
                      sizeof(WarpSmem<TDW, KCAP>) * kWarpsPerBlock};
 }
 
@@ -749,6 +779,13 @@ extern "C" int ns_batch_launch(ns_batch* b, void* stream) {
         a.k1p1 = kK1 + 1.0f;
         a.zero = 0u;
         a.impacts = reinterpret_cast<const uint2*>(b->res->d_scratch);
+        a.any_scratch = (b->impact && b->ndist > 0) ? 1u : 0u;
+        {
+            // next-window L2 prefetch pays when the items of a window really run together: window-major
+            // order and enough queries to fill the machine (NSB200_L2_PREFETCH=0/1 overrides)
+            static const char* env = std::getenv("NSB200_L2_PREFETCH");
+            a.l2_prefetch = env ? (std::atoi(env) != 0 ? 1u : 0u) : (b->window_major && b->Q >= 256 ? 1u : 0u);
+        }
         a.hits = b->d_out_hits;
         a.nhits = b->d_out_n;
         a.found = b->d_out_found;

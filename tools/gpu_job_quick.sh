@@ -1,3 +1,3 @@
 set -x
-timeout 300 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
-timeout 120 python bench.py --steps 30 --warmup 5 --profile-mode 2>/dev/null
+timeout 240 python -m pytest tests -m gpu -x -q --timeout 60 2>&1 | tail -3
+timeout 150 python bench.py --steps 30 --warmup 5 --profile-mode 2>/dev/null | tail -1
