@@ -16,7 +16,6 @@
 
 #include "../../include/nextsearch_b200.h"
 #include "bm25_kernels.cuh"
-#include "bm25_stream.cuh"
 #include "host/common.hpp"
 #include "host/segment_io.hpp"
 
@@ -71,7 +70,7 @@ struct SegState {
 
 struct IndexState {
     int device = 0;
-    uint32_t tile_docs = 2048;
+    uint32_t tile_docs = kTileDocs;
     std::vector<SegState> segs;  // ascending gseg
     std::unordered_map<uint32_t, uint32_t> slot_of;
     DevSeg* d_segs = nullptr;
@@ -115,7 +114,7 @@ struct BatchRes {
 
 struct ns_index {
     int device = 0;
-    uint32_t tile_docs = 2048;
+    uint32_t tile_docs = kTileDocs;
     std::mutex mu;
     std::shared_ptr<IndexState> live;
     std::vector<SegState> staged;
@@ -539,24 +538,9 @@ struct KernelCfg {
     int threads = kThreads;
 };
 
-// NSB200_KERNEL=stream selects the chunk-stream kernel (bm25_stream.cuh); default is the slice-nest kernel.
-bool use_nest_kernel() {
-    static const bool nest = [] {
-        const char* s = std::getenv("NSB200_KERNEL");
-        return !(s && std::strcmp(s, "stream") == 0);
-    }();
-    return nest;
-}
-
 template <int TDW, int KCAP, bool FAST, bool IMPACT, int NG>
 KernelCfg cfg_of() {
-    if (use_nest_kernel())
-        return KernelCfg{(const void*)bm25_score_topk_kernel<TDW, KCAP, FAST, IMPACT, NG>,
-                         sizeof(WarpSmem<TDW, KCAP>) * kWarpsPerBlock};
-    if (NG > 1)  // more than 32 terms for one (query, segment): the nest kernel's two register groups
-        return KernelCfg{(const void*)bm25_score_topk_kernel<TDW, KCAP, FAST, IMPACT, NG>,
-                         sizeof(WarpSmem<TDW, KCAP>) * kWarpsPerBlock};
-    return KernelCfg{(const void*)bm25_stream_kernel<TDW, KCAP, FAST, IMPACT>,
+    return KernelCfg{(const void*)bm25_score_topk_kernel<TDW, KCAP, FAST, IMPACT, NG>,
                      sizeof(WarpSmem<TDW, KCAP>) * kWarpsPerBlock};
 }
 
@@ -568,8 +552,8 @@ KernelCfg pick_kernel_tk(bool fast, bool impact) {
 
 // wide: some (query, segment) has more than 32 terms (two 32-term register groups per lane)
 KernelCfg pick_kernel(uint32_t k, bool fast, bool impact, bool wide) {
-    if (wide) return k <= 16 ? pick_kernel_tk<2048, 16, 2>(fast, impact) : pick_kernel_tk<2048, 104, 2>(fast, impact);
-    return k <= 16 ? pick_kernel_tk<2048, 16, 1>(fast, impact) : pick_kernel_tk<2048, 104, 1>(fast, impact);
+    if (wide) return k <= 16 ? pick_kernel_tk<kTileDocs, 16, 2>(fast, impact) : pick_kernel_tk<kTileDocs, 104, 2>(fast, impact);
+    return k <= 16 ? pick_kernel_tk<kTileDocs, 16, 1>(fast, impact) : pick_kernel_tk<kTileDocs, 104, 1>(fast, impact);
 }
 
 }  // namespace
