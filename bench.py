@@ -116,6 +116,23 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+NCU_SUMMARY = os.path.join(ROOT, "profiles", "r1_v9_final_ncu.txt")
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE score-kernel launch on this workload, from the
+    committed `ncu --set full` capture of the same command (profiles/); None when the file is absent."""
+    try:
+        tot = 0.0
+        for ln in open(NCU_SUMMARY):
+            f = ln.split()
+            if f and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                tot += float(f[2]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[f[1]]
+        return tot or None
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -307,6 +324,8 @@ def ours(args, rank, world, local_rank):
         ev0.record(stream)
         for i in range(W, W + K):
             step(i)
+        if world > 1:
+            searcher.drain()  # the last batches' all-gather + merge (exchange stream) are inside the timed region
         ev1.record(stream)
         sync_all()
         sampler.stop_flag = True
@@ -431,7 +450,9 @@ def ours(args, rank, world, local_rank):
                             "lexicon, prepare, H2D, kernels, D2H per call; `callers` host threads issue the calls"},
             "gpu_launches": launches_per_step * K,
             "roofline": {"bound": "hbm", "achieved": ach_local, "peak": peak, "unit": "GB/s",
-                         "frac": ach_local / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": ach_local / peak, "traffic": (ncu_traffic() if world == 1 else None),
+                         "traffic_source": "profiles/r1_v9_final_ncu.txt (ncu --set full, same command, one launch)",
+                         "peak_source": peak_src,
                          "kernel": "bm25_score_topk_kernel",
                          "algorithmic_bytes_per_launch": sum(alg_bytes) / max(1, len(alg_bytes)),
                          "kernel_ms": sum(k_ms[i] for i in used) / max(1, len(used)),

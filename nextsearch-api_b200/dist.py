@@ -77,6 +77,7 @@ class ShardedBatch:
     blob_bytes: int
     off_n: int
     off_f: int
+    comm_done: "object" = None  # torch event: this batch's all-gather + merge have finished (exchange stream)
 
 
 class ShardedSearcher:
@@ -87,6 +88,8 @@ class ShardedSearcher:
         self.torch, self.dist = torch, dist
         self.rank, self.world, self.device, self.group = rank, world, device, group
         self.engine = Engine(index_dir, device=device, rank=rank, world=world)
+        self.comm_stream = None  # exchange stream (all-gather + merge), created on first sharded launch
+        self._last_comm = None
 
     def reload(self) -> bool:
         return self.engine.reload()
@@ -108,26 +111,53 @@ class ShardedSearcher:
             blob_bytes=nbytes.value, off_n=off_n.value, off_f=off_f.value)
 
     def launch(self, sb: ShardedBatch) -> None:
-        """score+top-k on this rank's segments -> all-gather -> merge, all on torch's current stream."""
+        """score+top-k on this rank's segments (torch's current stream) -> all-gather -> merge.
+
+        With more than one rank the exchange (NCCL all-gather of the result blobs + device merge) runs on
+        its own stream behind an event, so the NEXT batch's score kernel — which does not depend on it —
+        is not held back by the latency-bound collective: the exchange of batch i lands in the tail of the
+        score kernel of batch i+1, where SMs are idle anyway.  `fetch` / `drain` order later work after it."""
         torch, dist = self.torch, self.dist
+        cur = torch.cuda.current_stream(self.device)
         # torch's default stream has handle 0, which ns_batch_launch reads as "the batch's own stream";
-        # name it explicitly (cudaStreamLegacy == 0x1) so that the kernels, the all-gather and the merge
-        # are ordered on ONE stream — otherwise NCCL may read the local blob while it is still written
-        stream = torch.cuda.current_stream(self.device).cuda_stream or 1
+        # name it explicitly (cudaStreamLegacy == 0x1) so that everything is ordered on torch's streams
+        stream = cur.cuda_stream or 1
+        if sb.comm_done is not None:
+            cur.wait_event(sb.comm_done)  # the previous exchange of this batch still reads its result blob
         sb.batch.launch(stream)
-        if self.world > 1:
-            dist.all_gather_into_tensor(sb.gathered, sb.local_blob, group=self.group)
-            src = sb.gathered
-        else:
-            src = sb.local_blob
         lib = _lib.load()
         base = sb.out.data_ptr()
-        check(lib.ns_merge_blobs_device(self.device, sb.Q, sb.k, self.world, C.c_void_p(src.data_ptr()),
-                                        sb.blob_bytes, sb.off_n, sb.off_f, C.c_void_p(base),
-                                        C.c_void_p(base + sb.off_n), C.c_void_p(base + sb.off_f),
-                                        C.c_void_p(stream) if stream else None))
+        if self.world == 1:
+            check(lib.ns_merge_blobs_device(self.device, sb.Q, sb.k, 1, C.c_void_p(sb.local_blob.data_ptr()),
+                                            sb.blob_bytes, sb.off_n, sb.off_f, C.c_void_p(base),
+                                            C.c_void_p(base + sb.off_n), C.c_void_p(base + sb.off_f), C.c_void_p(stream)))
+            return
+        if self.comm_stream is None:
+            self.comm_stream = torch.cuda.Stream(device=self.device)
+        cs = self.comm_stream
+        scored = torch.cuda.Event()
+        scored.record(cur)
+        cs.wait_event(scored)
+        with torch.cuda.stream(cs):
+            dist.all_gather_into_tensor(sb.gathered, sb.local_blob, group=self.group)
+            check(lib.ns_merge_blobs_device(self.device, sb.Q, sb.k, self.world, C.c_void_p(sb.gathered.data_ptr()),
+                                            sb.blob_bytes, sb.off_n, sb.off_f, C.c_void_p(base),
+                                            C.c_void_p(base + sb.off_n), C.c_void_p(base + sb.off_f),
+                                            C.c_void_p(cs.cuda_stream)))
+            sb.comm_done = torch.cuda.Event()
+            sb.comm_done.record(cs)
+        sb.gathered.record_stream(cs)
+        sb.out.record_stream(cs)
+        self._last_comm = sb.comm_done
+
+    def drain(self) -> None:
+        """Order torch's current stream after every exchange launched so far."""
+        if self._last_comm is not None:
+            self.torch.cuda.current_stream(self.device).wait_event(self._last_comm)
 
     def fetch(self, sb: ShardedBatch) -> BatchResult:
+        if sb.comm_done is not None:
+            self.torch.cuda.current_stream(self.device).wait_event(sb.comm_done)
         hits, nhits, found = unpack_blob(sb.out.cpu().numpy(), sb.Q, sb.k)  # one D2H copy
         return BatchResult(hits, nhits, found, sb.has_found, sb.k)
 
