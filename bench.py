@@ -369,6 +369,13 @@ def ours(args, rank, world, local_rank):
         thread-safe: while one call's kernels run, another call's tokenise/lexicon/prepare proceeds).
         Every call copies its descriptors H2D and its results D2H.  Returns (seconds, last result)."""
         last_box = [None]
+        if world > 1 and callers > 1:
+            # sharded: one caller per rank (the collectives must be issued in the same order on every rank);
+            # search_many prepares batch i+1 on the host while the GPUs work on batch i
+            t0 = time.perf_counter()
+            res = searcher.search_many([batches[i % nb] for i in range(e2e_steps)], TOPK)
+            torch.cuda.synchronize(dev)
+            return time.perf_counter() - t0, res[-1]
         if callers <= 1 or world > 1:
             t0 = time.perf_counter()
             for i in range(e2e_steps):
@@ -404,7 +411,7 @@ def ours(args, rank, world, local_rank):
     if world > 1:
         dist.barrier()
     e2e_single_s, last = run_e2e(1)
-    callers = 1 if world > 1 else max(1, args.e2e_callers)
+    callers = 2 if world > 1 else max(1, args.e2e_callers)  # world > 1: "2" = search_many's two batches in flight
     if callers > 1:
         run_e2e(callers)  # warm the extra callers' pooled buffers
         e2e_s, last = run_e2e(callers)
@@ -446,8 +453,12 @@ def ours(args, rank, world, local_rank):
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "callers": callers,
                     "single_caller_value": e2e_steps * BATCH_Q / e2e_single_s,
-                    "path": "Engine.search_batch(query strings) -> ns_engine_search_batch_packed: tokenise, "
-                            "lexicon, prepare, H2D, kernels, D2H per call; `callers` host threads issue the calls"},
+                    "path": ("Engine.search_batch(query strings) -> ns_engine_search_batch_packed: tokenise, "
+                             "lexicon, prepare, H2D, kernels, D2H per call; `callers` host threads issue the calls"
+                             if world == 1 else
+                             "ShardedSearcher.search_many(query strings): per batch tokenise, lexicon, prepare, H2D, "
+                             "kernels, all-gather, merge, D2H on every rank; the host work of batch i+1 overlaps the "
+                             "GPUs on batch i (`callers` = batches in flight per rank)")},
             "gpu_launches": launches_per_step * K,
             "roofline": {"bound": "hbm", "achieved": ach_local, "peak": peak, "unit": "GB/s",
                          "frac": ach_local / peak, "traffic": (ncu_traffic() if world == 1 else None),

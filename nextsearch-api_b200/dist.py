@@ -161,6 +161,23 @@ class ShardedSearcher:
         hits, nhits, found = unpack_blob(sb.out.cpu().numpy(), sb.Q, sb.k)  # one D2H copy
         return BatchResult(hits, nhits, found, sb.has_found, sb.k)
 
+    def search_many(self, batches: Sequence[Sequence[str]], k: int = 10):
+        """Several query batches, one result each, with the host front end of batch i+1 (tokenise, lexicon,
+        prepare, H2D) running while the GPU works on batch i.  Every rank must call it with the same batches
+        (one collective per batch, issued in the same order everywhere)."""
+        out, prev = [], None
+        for qs in batches:
+            sb = self.prepare(qs, k)
+            self.launch(sb)
+            if prev is not None:
+                out.append(self.fetch(prev))
+                prev.batch.close()
+            prev = sb
+        if prev is not None:
+            out.append(self.fetch(prev))
+            prev.batch.close()
+        return out
+
     def search_batch(self, queries: Sequence[str], k: int = 10) -> BatchResult:
         sb = self.prepare(queries, k)
         self.launch(sb)
