@@ -482,13 +482,13 @@ void build_items(ns_batch* b, uint32_t forced) {
     // items are ordered by window first, so that all resident warps sweep the same doc range of
     // the index at the same time and the hot posting slices are served from L2.
     uint32_t window = 16;  // measured best on 1M docs x 4096 queries (profiles/r1_v4_summary.md); 0 = query-major
-    // Items per query: ~10 items per resident warp over the whole batch, at least tiles/16 (windows of
-    // <= 16 tiles keep the batch's hot slices in L2), at most tiles/4 — and at most 16 for small batches,
+    // Items per query: ~10 items per resident warp over the whole batch, at least tiles/24 (windows of
+    // <= 24 tiles keep the batch's hot slices in L2), at most tiles/4 — and at most 16 for small batches,
     // where all items of a query run at the same time and serialise on the query's result-list lock.
     {
         const uint64_t warps = (uint64_t)b->owner->sm_count * 24;
         uint64_t ns = warps * 10 / std::max<uint32_t>(1, Q);
-        ns = std::max<uint64_t>(ns, (tiles + 15) / 16);
+        ns = std::max<uint64_t>(ns, (tiles + 23) / 24);
         ns = std::min<uint64_t>(ns, std::max<uint32_t>(1, tiles / 4));
         if (Q < 256) ns = std::min<uint64_t>(ns, 16);
         ns = std::max<uint64_t>(1, ns);
