@@ -349,6 +349,29 @@ def test_sharded_blobs_merge_on_device(workdir):
             e.close()
 
 
+def test_sharded_searcher_single_rank_pipeline(workdir):
+    """ShardedSearcher at world 1 (no collective): launch -> merge of the single blob -> fetch, and the
+    pipelined search_many (host front end of batch i+1 while the GPU works on batch i) — every batch of
+    the stream must equal the oracle, in order."""
+    pytest.importorskip("torch")
+    from nextsearch_api_b200.dist import ShardedSearcher
+
+    spec = nsb200.CorpusSpec(vocab=4000)
+    case = make_case(workdir, "eightseg_s", spec, 8000, 8)
+    s = ShardedSearcher(case.path, 0, 0, 1)
+    assert s.reload(), s.engine.last_error
+    batches = [nsb200.make_queries(spec, 200, 1, 5, seed=21 + i) + EDGE_QUERIES for i in range(4)]
+    one = s.search_batch(batches[0], 10)
+    assert_same_as_oracle(one, case.oracle, batches[0], 10)
+    many = s.search_many(batches, 10)
+    assert len(many) == len(batches)
+    for qs, res in zip(batches, many):
+        assert_same_as_oracle(res, case.oracle, qs, 10)
+    for res, qs in zip(s.search_many(batches[:2], 100), batches[:2]):
+        assert_same_as_oracle(res, case.oracle, qs, 100)
+    s.engine.close()
+
+
 def test_high_df_top100(workdir):
     """BASELINE configs[3]: every query contains a very frequent term (df > 10 % of the corpus), k=100."""
     spec = nsb200.CorpusSpec(vocab=20_000)
