@@ -244,7 +244,9 @@ template <class GetQuery>
 void resolve_all(ns_engine* e, uint32_t Q, GetQuery get, Resolved& out) {
     std::call_once(e->pool_once, [&] { e->pool.reset(new WorkPool(std::max(0, std::min(hw_threads(), 8) - 1))); });
     static const int max_nt = std::getenv("NSB200_HOST_THREADS") ? std::atoi(std::getenv("NSB200_HOST_THREADS")) : 1 << 20;
-    const int nt = std::max(1, std::min(std::min(e->pool->workers() + 1, max_nt), (int)(Q / 256) + 1));
+    // a sharded engine is one of `world` processes on the same box: take a 1/world share of the cores
+    const int share = std::max(1, hw_threads() / std::max(1, e->world));
+    const int nt = std::max(1, std::min(std::min(std::min(e->pool->workers() + 1, max_nt), share), (int)(Q / 256) + 1));
     std::vector<std::vector<ns_qterm>> per((size_t)nt);
     std::vector<uint32_t> cnt(Q, 0);
     out.has.assign(Q, 0);
