@@ -372,6 +372,28 @@ def test_sharded_searcher_single_rank_pipeline(workdir):
     s.engine.close()
 
 
+def test_result_list_lock_under_contention(workdir):
+    """Few heavy queries cut into 64 items each: all items of a query run at the same time and merge into
+    ONE shared result list under the per-query spin lock.  60 launches of the same batch must each give
+    the oracle's answer (a lost update, a torn list or a warp that lost convergence in the spin would not)."""
+    spec = nsb200.CorpusSpec(vocab=60_000)
+    case = make_case(workdir, "mid200k_lock", spec, 200_000, 1)
+    e = nsb200.Engine(case.path, device=0)
+    assert e.reload(), e.last_error
+    qs = nsb200.make_queries(spec, 6, 2, 5, seed=3, head_ranks=20)
+    q_off, terms, has = e.resolve_batch(qs)
+    for k in (10, 100):
+        b = e.index.prepare(q_off, terms, k)
+        b.set_splits(64)
+        for _ in range(60):
+            b.launch()
+            hits, nhits, found = b.fetch()
+            res = nsb200.BatchResult(hits.copy(), nhits.copy(), found.copy(), has, nsb200.clamp_k(k))
+            assert_same_as_oracle(res, case.oracle, qs, k)
+        b.close()
+    e.close()
+
+
 def test_high_df_top100(workdir):
     """BASELINE configs[3]: every query contains a very frequent term (df > 10 % of the corpus), k=100."""
     spec = nsb200.CorpusSpec(vocab=20_000)
