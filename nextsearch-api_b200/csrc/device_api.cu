@@ -596,15 +596,25 @@ extern "C" int ns_batch_prepare(ns_index* idx, uint32_t Q, int k_in, const uint6
     bool scan_always = false;
     bool fast = true;
     for (auto& sg : st->segs) fast = fast && sg.norm_in_range;
+    uint32_t memo_seg = 0xFFFFFFFFu;
+    int64_t memo_slot = -1;
+    {
+        auto it = st->slot_of.find(memo_seg);
+        if (it != st->slot_of.end()) memo_slot = (int64_t)it->second;
+    }
     for (uint32_t q = 0; q < Q; q++) {
         if (q_off[q + 1] < q_off[q]) { set_error("ns_batch_prepare: q_off not monotone"); return NS_ERR_INVALID; }
         uint32_t prev_slot = 0, in_seg = 0;
         bool have_prev = false;
         for (uint64_t e = q_off[q]; e < q_off[q + 1]; e++) {
             const ns_qterm& t = terms[e];
-            auto it = st->slot_of.find(t.seg);
-            if (it == st->slot_of.end()) continue;  // another rank's segment
-            const uint32_t slot = it->second;
+            if (t.seg != memo_seg) {  // terms come grouped by segment: one map lookup per run
+                auto it = st->slot_of.find(t.seg);
+                memo_seg = t.seg;
+                memo_slot = it == st->slot_of.end() ? -1 : (int64_t)it->second;
+            }
+            if (memo_slot < 0) continue;  // another rank's segment
+            const uint32_t slot = (uint32_t)memo_slot;
             const SegState& sg = st->segs[slot];
             if (t.row >= sg.T) { set_error("ns_batch_prepare: row out of range"); return NS_ERR_INVALID; }
             if (have_prev && slot < prev_slot) { set_error("ns_batch_prepare: terms of a query must be ordered by segment"); return NS_ERR_INVALID; }

@@ -81,18 +81,22 @@ void json_double(double v, std::string& out) {
 // Resolve one query against the owned segments.  Emits terms ordered by (segment asc, query order).
 // Returns whether the reference would compute "found" (base_terms and segments non-empty).
 bool resolve_one(const ns_engine* e, const char* query, std::vector<ns_qterm>& out) {
-    static thread_local std::vector<std::string> terms;
-    query_terms(query, terms);
-    if (terms.empty() || e->seg_names.empty()) return false;  // src/api_engine.cpp:407
+    static thread_local std::string buf;
+    static thread_local std::vector<TokSpan> spans;
+    static thread_local std::vector<uint64_t> hashes;
+    query_term_spans(query, buf, spans);
+    if (spans.empty() || e->seg_names.empty()) return false;  // src/api_engine.cpp:407
+    hashes.resize(spans.size());
+    for (size_t i = 0; i < spans.size(); i++) hashes[i] = term_hash(buf.data() + spans[i].off, spans[i].len);  // once per token
     for (size_t si = 0; si < e->segs.size(); si++) {
         const HostSegment* seg = e->segs[si].get();
         if (!seg) continue;
-        for (auto& t : terms) {  // qweight 1.0f: src/api_engine.cpp:420
-            auto it = seg->lex.find(t);
-            if (it == seg->lex.end()) continue;  // :454-455
-            const LexRow& r = seg->rows[it->second];
+        for (size_t i = 0; i < spans.size(); i++) {  // qweight 1.0f: src/api_engine.cpp:420
+            const int64_t row = seg->table.find(buf.data() + spans[i].off, spans[i].len, hashes[i]);
+            if (row < 0) continue;  // :454-455
+            const LexRow& r = seg->rows[(size_t)row];
             if (r.df == 0) continue;  // :458
-            out.push_back(ns_qterm{(uint32_t)si, it->second, r.idf, 1.0f});
+            out.push_back(ns_qterm{(uint32_t)si, (uint32_t)row, r.idf, 1.0f});
         }
     }
     return true;

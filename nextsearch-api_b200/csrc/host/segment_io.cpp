@@ -222,6 +222,7 @@ bool load_segment(const std::string& segdir, HostSegment& s, int nthreads) {
         s.rows[i].idf = bm25_idf(s.N, s.rows[i].df);
         s.lex.emplace(std::move(terms[i]), i);  // emplace: first entry for a term wins
     }
+    s.table.build(s.lex);
     return true;
 }
 

@@ -4,6 +4,7 @@
 // lexicon rows are kept in an array so that a row index can cross the C ABI.
 #pragma once
 #include <cstdint>
+#include <cstring>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -19,6 +20,50 @@ struct LexRow {
     float idf = 0.0f;      // bm25_idf(N, df) — src/api_engine.cpp:45-47, host logf
 };
 
+// 64-bit FNV-1a of a term's bytes: computed once per query token, reused for every segment's table.
+inline uint64_t term_hash(const char* p, size_t n) {
+    uint64_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < n; i++) h = (h ^ (unsigned char)p[i]) * 1099511628211ull;
+    return h;
+}
+
+// Flat open-addressing view of HostSegment::lex for the query front end (one cache line per probe,
+// hash computed by the caller).  Keys point into the map's own nodes, which never move.
+struct TermTable {
+    struct Slot {
+        uint64_t h = 0;
+        const std::string* key = nullptr;  // nullptr = empty
+        uint32_t row = 0;
+        uint32_t pad = 0;
+    };
+    std::vector<Slot> slots;
+    uint64_t mask = 0;
+
+    void build(const std::unordered_map<std::string, uint32_t>& lex) {
+        size_t cap = 16;
+        while (cap < lex.size() * 2 + 1) cap <<= 1;
+        slots.assign(cap, Slot{});
+        mask = cap - 1;
+        for (auto& kv : lex) {
+            const uint64_t h = term_hash(kv.first.data(), kv.first.size());
+            size_t i = (size_t)(h & mask);
+            while (slots[i].key) i = (i + 1) & mask;
+            slots[i].h = h;
+            slots[i].key = &kv.first;
+            slots[i].row = kv.second;
+        }
+    }
+    // row of the term, or -1
+    int64_t find(const char* p, size_t n, uint64_t h) const {
+        if (slots.empty()) return -1;
+        for (size_t i = (size_t)(h & mask);; i = (i + 1) & mask) {
+            const Slot& s = slots[i];
+            if (!s.key) return -1;
+            if (s.h == h && s.key->size() == n && std::memcmp(s.key->data(), p, n) == 0) return (int64_t)s.row;
+        }
+    }
+};
+
 struct HostSegment {
     std::string dir;
     uint32_t N = 0;        // stats.bin
@@ -28,6 +73,7 @@ struct HostSegment {
     std::vector<uint64_t> uid_off;   // [n+1]
     std::vector<LexRow> rows;
     std::unordered_map<std::string, uint32_t> lex;  // term -> row (first occurrence wins, like emplace)
+    TermTable table;                                // the same mapping, flat (built by load_segment)
     std::vector<uint64_t> postings;  // interleaved {u32 docId, u32 tf} = file bytes
     bool use_barrels = false;
     uint32_t barrel_count = 0, terms_per_barrel = 0;
