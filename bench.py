@@ -31,7 +31,8 @@ sys.path.insert(0, ROOT)
 
 METRIC = "bm25_top10_queries_per_sec_1M_docs"
 UNIT = "queries/s"
-NDOCS = 1_000_000
+NDOCS = int(os.environ.get("NSB200_BENCH_DOCS", "1000000"))   # default = BASELINE configs[1]/[2]; 8000000 with
+SEGS_SHARDED = int(os.environ.get("NSB200_BENCH_SEGS", "8"))  # NSB200_BENCH_SEGS=64 is configs[4] (8M docs, 64 segments)
 BATCH_Q = 4096
 TOPK = 10
 BENCH_DIR = os.environ.get("NSB200_BENCH_DIR", "/dev/shm/nsb200_bench")
@@ -193,7 +194,7 @@ def reference_arm(args, rank, world):
         return
     from oracle import oracle as orc
 
-    nseg = 1 if args.gpus == 1 else 8
+    nseg = 1 if args.gpus == 1 else SEGS_SHARDED
     path = ensure_index(nseg)
     cores = os.cpu_count() or 1
     replicas = max(1, min(cores, args.ref_replicas or cores))
@@ -239,8 +240,13 @@ def reference_arm(args, rank, world):
 
 
 def workload_config(n_gpus, nseg):
-    return {"workload": ("BASELINE configs[1]: 1M docs, 1 segment" if nseg == 1 else
-                         "BASELINE configs[2]: 1M docs in 8 segments, segment-sharded + NCCL all-gather merge"),
+    if NDOCS != 1_000_000 or nseg not in (1, 8):
+        wl = f"BASELINE configs[4]-style: {NDOCS} docs in {nseg} segments, segment-sharded + NCCL all-gather merge"
+    elif nseg == 1:
+        wl = "BASELINE configs[1]: 1M docs, 1 segment"
+    else:
+        wl = "BASELINE configs[2]: 1M docs in 8 segments, segment-sharded + NCCL all-gather merge"
+    return {"workload": wl,
             "docs": NDOCS, "segments": nseg, "batch_queries": BATCH_Q, "terms_per_query": "1-5", "k": TOPK,
             "corpus": "shifted Zipf s=1 q=25, V=400000, doc_len U[100,250), seed 20260101; query seeds 7+i",
             "l2_policy": "index (1.35 GB postings) is larger than L2; distinct query batches rotate between steps",
@@ -268,7 +274,7 @@ def ours(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = local_rank
     torch.cuda.set_device(dev)
-    nseg = 1 if world == 1 else 8
+    nseg = 1 if world == 1 else SEGS_SHARDED
 
     if rank == 0:
         path = ensure_index(nseg)
