@@ -63,6 +63,38 @@ def test_resolve_batch_emits_reference_lookup(small_case):
     e.close()
 
 
+def test_batched_front_end_equals_token_by_token_lookup(small_case):
+    """The batched resolve has its own allocation-free tokenizer and a flat hash table: on messy random
+    strings it must emit exactly what query_terms() + a per-term lexicon lookup give, segment by segment."""
+    import random
+
+    rng = random.Random(5)
+    e = nsb200.Engine(small_case.path, device=None)
+    assert e.reload()
+    alphabet = ["t1", "T2", "t17", "t2999", "t3000", "nosuch", "the", "AND", "a", "b7", "x", "t5,t6", "t8-T9", "caf\u00e9",
+                "\t", "  ", "!", "t12_t13", "of", "It", "THIS", "t44.", "(t45)", "t1t2", "0", "00", "t007"]
+    qs = [" ".join(rng.choice(alphabet) for _ in range(rng.randint(0, 9))) for _ in range(600)] + ["", " ", "the", "t1"]
+    q_off, terms, has = e.resolve_batch(qs)
+    for q, text in enumerate(qs):
+        toks = nsb200.query_terms(text)
+        assert bool(has[q]) == (len(toks) > 0), text
+        want = []
+        for seg in range(2):
+            for t in toks:
+                df, _cnt = e.term_stats(seg, t)
+                if df > 0:
+                    want.append((seg, t))
+        got = terms[int(q_off[q]):int(q_off[q + 1])]
+        assert len(got) == len(want), (text, toks)
+        for g, (seg, t) in zip(got, want):
+            assert int(g["seg"]) == seg
+            # same row <=> same term: compare through a one-term resolve
+            _, one, _ = e.resolve_batch([t])
+            rows = {int(x["seg"]): int(x["row"]) for x in one}
+            assert int(g["row"]) == rows[seg], (text, t)
+    e.close()
+
+
 def test_host_only_engine_refuses_to_search(small_case):
     e = nsb200.Engine(small_case.path, device=None)
     assert e.reload()
