@@ -481,7 +481,7 @@ void build_items(ns_batch* b, uint32_t forced) {
     // NSB200_WINDOW_TILES=w: tile-major order — every query is cut into windows of ~w tiles and
     // items are ordered by window first, so that all resident warps sweep the same doc range of
     // the index at the same time and the hot posting slices are served from L2.
-    uint32_t window = 16;  // measured best on 1M docs x 4096 queries (profiles/r1_v4_summary.md); 0 = query-major
+    uint32_t window = 24;  // tiles per item (set below from the batch shape); 0 = query-major
     // Items per query: ~10 items per resident warp over the whole batch, at least tiles/24 (windows of
     // <= 24 tiles keep the batch's hot slices in L2), at most tiles/4 — and at most 16 for small batches,
     // where all items of a query run at the same time and serialise on the query's result-list lock.
@@ -682,7 +682,7 @@ extern "C" int ns_batch_prepare(ns_index* idx, uint32_t Q, int k_in, const uint6
     const size_t sz_terms = align_up(std::max<size_t>(1, kept.size()) * sizeof(DevTerm));
     const size_t sz_items = align_up(std::max<size_t>(1, b->items_cap) * sizeof(DevItem));
     const size_t sz_list = align_up(((size_t)Q + 1) * 4);
-    const size_t sz_counter = align_up(4 + (size_t)Q * 4);  // work-queue head + qthr[Q], zeroed per launch
+    const size_t sz_counter = align_up(4 + (size_t)Q * 4);  // work-queue head + per-query locks, zeroed per launch
     const size_t sz_dist = align_up(std::max<size_t>(1, dist.size()) * sizeof(DevDistinct));
     const size_t sz_dstart = align_up(dstart.size() * 4);
     b->off_items = sz_qoff + sz_terms;
