@@ -117,7 +117,7 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-NCU_SUMMARY = os.path.join(ROOT, "profiles", "r1_v11_final_ncu.txt")
+NCU_SUMMARY = os.path.join(ROOT, "profiles", "r1_v12_final_ncu.txt")
 
 
 def ncu_traffic():
@@ -468,7 +468,7 @@ def ours(args, rank, world, local_rank):
             "gpu_launches": launches_per_step * K,
             "roofline": {"bound": "hbm", "achieved": ach_local, "peak": peak, "unit": "GB/s",
                          "frac": ach_local / peak, "traffic": (ncu_traffic() if world == 1 else None),
-                         "traffic_source": "profiles/r1_v11_final_ncu.txt (ncu --set full, same command, one launch)",
+                         "traffic_source": "profiles/r1_v12_final_ncu.txt (ncu --set full, same command, one launch)",
                          "peak_source": peak_src,
                          "kernel": "bm25_score_topk_kernel",
                          "algorithmic_bytes_per_launch": sum(alg_bytes) / max(1, len(alg_bytes)),
