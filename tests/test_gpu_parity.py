@@ -103,6 +103,24 @@ def test_weighted_terms_via_abi(small_case, small_engine):
         assert np.array_equal(h2["doc"][q, :n], h1["doc"][q, :n])
 
 
+def test_more_than_32_terms_per_query(small_case, small_engine):
+    """The reference's semantic expansion yields up to 40 terms per query (src/api_engine.cpp:417); a batch
+    with more than 32 terms for one (query, segment) runs the two-register-group kernel variant (NG = 2).
+    Wide and narrow queries mixed, duplicates included, k = 10 and 100."""
+    import random
+
+    rng = random.Random(9)
+    wide = [" ".join(f"t{rng.randint(1, 400)}" for _ in range(n)) for n in (33, 40, 47, 64, 36, 50)]
+    wide.append(" ".join(f"t{i}" for i in range(1, 41)))                 # 40 distinct head terms
+    wide.append(" ".join(["t3", "t7"] * 20))                             # 40 terms, two distinct
+    qs = wide + nsb200.make_queries(small_case.spec, 40, 1, 5, seed=13) + EDGE_QUERIES
+    for k in (10, 100):
+        assert_same_as_oracle(small_engine.search_batch(qs, k), small_case.oracle, qs, k)
+    # one more than the ABI limit is refused, not truncated
+    with pytest.raises(nsb200._lib.NsError):
+        small_engine.search_batch([" ".join(f"t{i}" for i in range(1, 66))], 10)
+
+
 def test_rejects_unsorted_postings():
     idx = nsb200.DeviceIndex(0)
     doc_len = np.full(16, 10, np.uint32)
