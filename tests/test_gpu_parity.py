@@ -121,6 +121,18 @@ def test_more_than_32_terms_per_query(small_case, small_engine):
         small_engine.search_batch([" ".join(f"t{i}" for i in range(1, 66))], 10)
 
 
+def test_empty_and_termless_batches(small_case, small_engine):
+    """Q = 0, and batches in which no query has a usable term (no item, no kernel work): like the reference,
+    results are empty, `found` is 0 and absent for the all-stopword / empty queries (src/api_engine.cpp:407)."""
+    res = small_engine.search_batch([], 10)
+    assert len(res.nhits) == 0 and len(res.found) == 0
+    qs = ["the of and", "", "a b c", "zzzz", "qqqq wwww"]
+    res = small_engine.search_batch(qs, 10)
+    assert_same_as_oracle(res, small_case.oracle, qs, 10)
+    assert list(res.nhits) == [0] * 5 and list(res.found) == [0] * 5
+    assert list(res.has_found) == [False, False, False, True, True]
+
+
 def test_rejects_unsorted_postings():
     idx = nsb200.DeviceIndex(0)
     doc_len = np.full(16, 10, np.uint32)
