@@ -130,6 +130,8 @@ struct ns_batch {
     uint32_t Q = 0, k = 0;
     uint32_t nitems = 0, max_split = 1;
     bool window_major = false;  // items ordered by doc window first (build_items)
+    bool implicit_items = false;  // window-major with one nsplit for all queries: the item list is order[] + arithmetic
+    uint32_t nsplit_all = 1;
     bool scan_always = false;
     bool fast = false;  // operand ranges validated + unit weights: FAST kernel variant
     bool impact = false;           // per-batch shared term scores (impact pre-pass)
@@ -514,19 +516,24 @@ void build_items(ns_batch* b, uint32_t forced) {
     std::vector<uint64_t> iw(Q);
     for (uint32_t q = 0; q < Q; q++) iw[q] = b->weight[q] / nsplit[q];
     std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return iw[x] > iw[y]; });
-    std::vector<DevItem> items;
-    items.reserve(nitems);
+    DevItem* h_items = reinterpret_cast<DevItem*>(b->res->h_in + b->off_items);
     b->window_major = window && !forced;
-    if (window && !forced) {
+    static const bool explicit_items = std::getenv("NSB200_EXPLICIT_ITEMS") != nullptr;
+    b->implicit_items = b->window_major && !explicit_items;
+    b->nsplit_all = maxs;
+    if (b->implicit_items) {
+        // every query has the same number of windows: item i = (order[i % Q], window i / Q); only order[] is uploaded
+        std::memcpy(h_items, order.data(), (size_t)Q * 4);
+    } else if (window && !forced) {
+        size_t at = 0;
         for (uint32_t sp = 0; sp < maxs; sp++)
             for (uint32_t q : order)
-                if (sp < nsplit[q]) items.push_back(DevItem{q, (sp << 16) | nsplit[q]});
+                if (sp < nsplit[q]) h_items[at++] = DevItem{q, (sp << 16) | nsplit[q]};
     } else {
+        size_t at = 0;
         for (uint32_t q : order)
-            for (uint32_t sp = 0; sp < nsplit[q]; sp++) items.push_back(DevItem{q, (sp << 16) | nsplit[q]});
+            for (uint32_t sp = 0; sp < nsplit[q]; sp++) h_items[at++] = DevItem{q, (sp << 16) | nsplit[q]};
     }
-    DevItem* h_items = reinterpret_cast<DevItem*>(b->res->h_in + b->off_items);
-    std::memcpy(h_items, items.data(), (size_t)nitems * sizeof(DevItem));
     std::memcpy(b->res->h_in + b->off_list, list_off.data(), ((size_t)Q + 1) * 4);
     b->nitems = nitems;
     b->max_split = maxs;
@@ -764,7 +771,10 @@ extern "C" int ns_batch_launch(ns_batch* b, void* stream) {
         a.total_tiles = b->st->total_tiles;
         a.qoff = b->d_qoff;
         a.terms = b->d_terms;
-        a.items = b->d_items;
+        a.items = b->implicit_items ? nullptr : b->d_items;
+        a.order = reinterpret_cast<const uint32_t*>(b->d_items);
+        a.nq = b->Q;
+        a.nsplit = b->nsplit_all;
         a.counter = b->d_counter;
         a.qlock = b->d_counter + 1;
         a.nitems = b->nitems;

@@ -383,17 +383,17 @@ static void scratch_free(orc_scratch* sc) { free(sc->score); free(sc->touched); 
 
 #define ORC_MAX_TERMS 256
 
-/* src/api_engine.cpp:369-505 with weights = 1.0f (semantic expansion disabled, :418-421).
+/* The scoring loop proper, src/api_engine.cpp:426-505, over an explicit (term, qweight) list — the
+ * reference's qterms_w (:410-421): the query's own terms with weight 1.0f, or SemanticIndex::expand's
+ * output when embeddings are loaded (src/semantic_embedding.cpp:148-229).
  * Returns the number of hits written (<= K), K = clamp(k,1,100) (:377). */
-static int search_impl(const orc_index* ix, orc_scratch* sc, const char* query, int k, orc_hit* hits,
-                       uint64_t* found, int* has_found) {
+static int search_terms_impl(const orc_index* ix, orc_scratch* sc, int nt, char* const* terms, const float* weights,
+                             int k, orc_hit* hits, uint64_t* found, int* has_found) {
     const float k1 = 1.2f, b = 0.75f;                                  /* :375-376 */
     const int K = k < 1 ? 1 : (k > 100 ? 100 : k);                     /* :377 */
-    char* terms[ORC_MAX_TERMS];
-    int nt = orc_query_terms(query, terms, ORC_MAX_TERMS);             /* :388-397 */
     *found = 0;
     *has_found = 0;
-    if (nt == 0 || ix->nseg == 0) return 0;                            /* :407 */
+    if (nt == 0 || ix->nseg == 0) return 0;                            /* :407, :424 */
     *has_found = 1;
     int nh = 0;
     uint64_t total_found = 0;
@@ -401,7 +401,7 @@ static int search_impl(const orc_index* ix, orc_scratch* sc, const char* query, 
         const orc_seg* seg = &ix->segs[si];
         uint32_t ntouched = 0;
         for (int t = 0; t < nt; t++) {                                 /* :449, query order, duplicates kept */
-            const float qweight = 1.0f;
+            const float qweight = weights ? weights[t] : 1.0f;         /* :451; 1.0f without expansion (:420) */
             const orc_lex* e = lex_find(seg, terms[t]);                /* :454-455 */
             if (!e) continue;
             if (e->df == 0) continue;                                  /* :458 */
@@ -429,8 +429,30 @@ static int search_impl(const orc_index* ix, orc_scratch* sc, const char* query, 
         for (uint32_t i = 0; i < ntouched; i++) sc->touched[sc->list[i]] = 0;
     }
     *found = total_found;                                              /* :505 */
+    return nh;
+}
+
+/* src/api_engine.cpp:369-505 with semantic expansion disabled (:418-421): tokenise, filter, weight 1.0f. */
+static int search_impl(const orc_index* ix, orc_scratch* sc, const char* query, int k, orc_hit* hits,
+                       uint64_t* found, int* has_found) {
+    char* terms[ORC_MAX_TERMS];
+    int nt = orc_query_terms(query, terms, ORC_MAX_TERMS);             /* :388-397 */
+    int nh = search_terms_impl(ix, sc, nt, terms, NULL, k, hits, found, has_found);
     for (int t = 0; t < nt; t++) free(terms[t]);
     return nh;
+}
+
+/* Weighted entry: the caller supplies qterms_w in the reference's order (tests take it from the compiled
+ * reference: oracle/ref_driver.cpp dumps SemanticIndex::expand's output next to every result). */
+int orc_search_weighted(const orc_index* ix, int nterms, const char* const* terms, const float* weights, int k,
+                        float* scores, uint32_t* segs, uint32_t* docs, uint64_t* found, int* has_found) {
+    if (nterms < 0 || nterms > ORC_MAX_TERMS) return -1;
+    orc_scratch* sc = scratch_new(ix);
+    orc_hit hits[100];
+    int n = search_terms_impl(ix, sc, nterms, (char* const*)terms, weights, k, hits, found, has_found);
+    for (int i = 0; i < n; i++) { scores[i] = hits[i].s; segs[i] = hits[i].seg; docs[i] = hits[i].doc; }
+    scratch_free(sc);
+    return n;
 }
 
 int orc_search(const orc_index* ix, const char* query, int k, float* scores, uint32_t* segs, uint32_t* docs,
