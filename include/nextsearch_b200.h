@@ -92,6 +92,34 @@ int ns_index_add_segment(ns_index* idx, uint32_t global_seg, uint32_t N, float a
                          const uint32_t* doc_len, uint32_t T, const uint64_t* term_begin,
                          const uint32_t* term_count, const void* postings, uint64_t P);
 
+/* Same with two options.
+ *   row_idf[T]   (may be NULL) the idf every row's resident term scores are built with; NULL means
+ *                bm25_idf(N, term_count[t]).  The host engine passes bm25_idf(N, LexEntry.df) of its lexicon
+ *                (src/api_engine.cpp:461), so its queries never need the per-batch pre-pass even if a writer
+ *                ever stored df != count.
+ *   flags        NS_SEG_DROP_RAW: keep only {docId, resident term score} per posting (built in place); halves
+ *                the segment's footprint.  A batch that names a row with an idf different from the resident
+ *                one is then refused with NS_ERR_STATE. */
+#define NS_SEG_DROP_RAW 1u
+int ns_index_add_segment_ex(ns_index* idx, uint32_t global_seg, uint32_t N, float avgdl,
+                            const uint32_t* doc_len, uint32_t T, const uint64_t* term_begin,
+                            const uint32_t* term_count, const float* row_idf, const void* postings, uint64_t P,
+                            uint32_t flags);
+
+/* Streamed form of the same upload (reference: load_segment_barrels, src/api_segment.cpp:69-103, reads 64
+ * inverted_bNNN.bin files): begin allocates the device posting array and a PINNED host buffer of P postings;
+ * the loader reads each barrel file straight into its place in ns_upload_buffer() and calls ns_upload_push for
+ * the finished range (thread-safe, asynchronous: the copies overlap the remaining file reads); finish waits
+ * for the copies and does what ns_index_add_segment_ex does.  finish and abort both free the ticket. */
+typedef struct ns_upload ns_upload;
+int ns_upload_begin(ns_index* idx, uint64_t P, ns_upload** out);
+void* ns_upload_buffer(ns_upload* u);
+int ns_upload_push(ns_upload* u, uint64_t first_posting, uint64_t count);
+int ns_upload_finish(ns_upload* u, uint32_t global_seg, uint32_t N, float avgdl, const uint32_t* doc_len,
+                     uint32_t T, const uint64_t* term_begin, const uint32_t* term_count, const float* row_idf,
+                     uint32_t flags);
+void ns_upload_abort(ns_upload* u);
+
 /* Atomically replace the searchable index with the staged segments
  * (reference: `segments = std::move(loaded)` src/api_engine.cpp:90).  In-flight
  * batches keep the index they started with.  On failure the previous index stays. */
@@ -135,7 +163,10 @@ int ns_batch_device_results(ns_batch* b, void** d_hits, void** d_nhits, void** d
 /* introspection for bench.py */
 uint64_t ns_batch_posting_count(const ns_batch* b);   /* Σ LexEntry.count over all (query, term, segment) */
 uint32_t ns_batch_num_launches(const ns_batch* b);    /* kernels one ns_batch_launch enqueues */
-float ns_batch_last_kernel_ms(ns_batch* b, int which); /* CUDA-event time of the last launch: 0 = score+topk, 1 = merge */
+float ns_batch_last_kernel_ms(ns_batch* b, int which); /* CUDA-event time of the last launch: 0 = zeroing + score+topk, 1 = what follows (merge) */
+void* ns_batch_stream(ns_batch* b);                   /* the batch's own cudaStream_t (what a NULL stream argument means) */
+uint64_t ns_batch_upload_bytes(const ns_batch* b);    /* host->device bytes prepare copied for this batch */
+uint64_t ns_batch_result_bytes(const ns_batch* b);    /* device->host bytes one fetch copies */
 int ns_batch_set_splits(ns_batch* b, uint32_t splits); /* 0 = auto */
 
 /* Merge `nlists` per-rank (or per-split) result sets on the device.
@@ -153,6 +184,48 @@ int ns_batch_result_blob(ns_batch* b, void** d_blob, uint64_t* bytes, uint64_t* 
 int ns_merge_blobs_device(int device, uint32_t Q, int k, uint32_t nlists, const void* d_blobs,
                           uint64_t blob_stride, uint64_t off_nhits, uint64_t off_found, void* d_out_hits,
                           void* d_out_nhits, void* d_out_found, void* stream);
+
+/* ------------------------------------------------------------------ */
+/* Multi-GPU: peer exchange of the per-GPU result blobs.               */
+/* (reference: the cross-segment state of src/api_engine.cpp:435,495 — */
+/*  the global top-K heap and the found sum — is all that is exchanged)*/
+/* ------------------------------------------------------------------ */
+/* Segments shard across GPUs; every GPU scores the same query batch against its own segments.  The score
+ * kernel itself stores each finished query's list into the gather buffer of every destination GPU (P2P stores
+ * over NVLink, no separate collective), raises a flag when its blob is complete, and a receiving GPU merges
+ * the `world` blobs under the total order once all flags of the step are up.
+ *   same process  : ns_exchange_attach_local (cudaDeviceEnablePeerAccess)
+ *   one process per GPU (torchrun): exchange the 64-byte handle of ns_exchange_ipc_handle out of band
+ *                   (e.g. torch.distributed.all_gather_object) and ns_exchange_attach_ipc it.
+ * A rank that attaches ITSELF (attach_local(x, x)) is a receiver: it waits and merges.  Every rank must use the
+ * same (world, max_queries, slots).  Steps are numbered by the caller, consecutive steps use consecutive
+ * slots; with launches and merges of one rank on ONE stream two slots suffice (a rank can be at most one
+ * step ahead of the slowest one, because its own merge of step i waits for everybody's step i). */
+typedef struct ns_exchange ns_exchange;
+#define NS_IPC_HANDLE_BYTES 64
+#define NS_MAX_PEERS 16
+int ns_exchange_create(int device, uint32_t world, uint32_t rank, uint32_t max_queries, uint32_t slots,
+                       ns_exchange** out);
+void ns_exchange_destroy(ns_exchange* x);
+int ns_exchange_ipc_handle(ns_exchange* x, void* handle /* NS_IPC_HANDLE_BYTES */);
+int ns_exchange_attach_ipc(ns_exchange* x, uint32_t peer_rank, const void* handle);
+int ns_exchange_attach_local(ns_exchange* x, ns_exchange* peer);
+/* ns_batch_launch whose score kernel also publishes to every attached destination. */
+int ns_batch_launch_exchange(ns_batch* b, ns_exchange* x, uint64_t step, void* stream);
+/* Receiver side of `step`, enqueued on `stream` (NULL = the exchange's own): wait until every rank's blob of
+ * the step has arrived, then merge the `world` blobs into the exchange's merged blob of slot step % slots
+ * (same layout as ns_batch_result_blob).
+ *   spin = 1: a one-warp kernel polls the arrival flags (bounded by the timeout) — the cross-process case,
+ *             where nothing else can order this stream after another process's kernel.  Enqueue it AFTER this
+ *             rank's own ns_batch_launch_exchange of the step.
+ *   spin = 0: the caller has ordered `stream` after every publisher's score kernel itself
+ *             (cudaStreamWaitEvent on events of the other devices, same process): no polling. */
+int ns_exchange_merge(ns_exchange* x, uint64_t step, uint32_t Q, int k, int spin, void* stream);
+int ns_exchange_result_device(ns_exchange* x, uint64_t step, void** d_blob);
+/* D2H of the merged result of `step` (waits for it).  NS_ERR_STATE if a rank's blob did not arrive within
+ * NSB200_EXCHANGE_TIMEOUT_MS (default 2000): the wait is bounded, a missing peer cannot hang the GPU. */
+int ns_exchange_fetch(ns_exchange* x, uint64_t step, uint32_t Q, int k, ns_hit* out_hits, uint32_t* out_nhits,
+                      uint64_t* out_found);
 
 /* ------------------------------------------------------------------ */
 /* Engine mirror (host).  Same surface as cord19::Engine for this path.*/

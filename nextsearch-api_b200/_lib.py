@@ -15,6 +15,8 @@ LIB_PATH = os.path.join(_HERE, "libnsb200.so")
 NS_OK = 0
 NS_MAX_K = 100
 NS_MAX_TERMS = 64
+NS_SEG_DROP_RAW = 1
+NS_IPC_HANDLE_BYTES = 64
 STATUS_NAMES = {0: "NS_OK", 1: "NS_ERR_INVALID", 2: "NS_ERR_CUDA", 3: "NS_ERR_IO", 4: "NS_ERR_FORMAT",
                 5: "NS_ERR_NOMEM", 6: "NS_ERR_STATE"}
 
@@ -50,6 +52,13 @@ SYMBOLS = {
     "ns_index_create": (C.c_int, [C.c_int, C.POINTER(_P)]),
     "ns_index_destroy": (None, [_P]),
     "ns_index_add_segment": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_float, _P, C.c_uint32, _P, _P, _P, C.c_uint64]),
+    "ns_index_add_segment_ex": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_float, _P, C.c_uint32, _P, _P, _P, _P, C.c_uint64,
+                                          C.c_uint32]),
+    "ns_upload_begin": (C.c_int, [_P, C.c_uint64, C.POINTER(_P)]),
+    "ns_upload_buffer": (_P, [_P]),
+    "ns_upload_push": (C.c_int, [_P, C.c_uint64, C.c_uint64]),
+    "ns_upload_finish": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_float, _P, C.c_uint32, _P, _P, _P, C.c_uint32]),
+    "ns_upload_abort": (None, [_P]),
     "ns_index_commit": (C.c_int, [_P]),
     "ns_index_abort": (C.c_int, [_P]),
     "ns_index_num_segments": (C.c_int, [_P]),
@@ -65,6 +74,18 @@ SYMBOLS = {
     "ns_batch_num_launches": (C.c_uint32, [_P]),
     "ns_batch_last_kernel_ms": (C.c_float, [_P, C.c_int]),
     "ns_batch_set_splits": (C.c_int, [_P, C.c_uint32]),
+    "ns_batch_stream": (_P, [_P]),
+    "ns_batch_upload_bytes": (C.c_uint64, [_P]),
+    "ns_batch_result_bytes": (C.c_uint64, [_P]),
+    "ns_exchange_create": (C.c_int, [C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(_P)]),
+    "ns_exchange_destroy": (None, [_P]),
+    "ns_exchange_ipc_handle": (C.c_int, [_P, _P]),
+    "ns_exchange_attach_ipc": (C.c_int, [_P, C.c_uint32, _P]),
+    "ns_exchange_attach_local": (C.c_int, [_P, _P]),
+    "ns_batch_launch_exchange": (C.c_int, [_P, _P, C.c_uint64, _P]),
+    "ns_exchange_merge": (C.c_int, [_P, C.c_uint64, C.c_uint32, C.c_int, C.c_int, _P]),
+    "ns_exchange_result_device": (C.c_int, [_P, C.c_uint64, C.POINTER(_P)]),
+    "ns_exchange_fetch": (C.c_int, [_P, C.c_uint64, C.c_uint32, C.c_int, _P, _P, _P]),
     "ns_merge_device": (C.c_int, [C.c_int, C.c_uint32, C.c_int, C.c_uint32, _P, _P, _P, _P, _P, _P, _P]),
     "ns_batch_result_blob": (C.c_int, [_P, C.POINTER(_P), _u64p, _u64p, _u64p]),
     "ns_merge_blobs_device": (C.c_int, [C.c_int, C.c_uint32, C.c_int, C.c_uint32, _P, C.c_uint64, C.c_uint64, C.c_uint64,

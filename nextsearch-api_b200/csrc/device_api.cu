@@ -16,6 +16,7 @@
 
 #include "../../include/nextsearch_b200.h"
 #include "bm25_kernels.cuh"
+#include "device_internal.hpp"
 #include "host/common.hpp"
 #include "host/segment_io.hpp"
 
@@ -39,11 +40,33 @@ inline size_t align_up(size_t x) { return (x + kAlign - 1) / kAlign * kAlign; }
 const float kK1 = 1.2f;
 const float kB = 0.75f;
 
+// Environment overrides, read ONCE when the index handle is created (never on the query path).
+struct Tunables {
+    bool no_pack = false, no_resident = false, no_fast = false, explicit_items = false, trace = false;
+    long item_postings = 0;   // NSB200_ITEM_POSTINGS (0 = default)
+    int window_tiles = -1;    // NSB200_WINDOW_TILES (-1 = from the batch shape)
+    int l2_prefetch = -1;     // NSB200_L2_PREFETCH (-1 = auto)
+    int impact = -1;          // NSB200_IMPACT (-1 = auto)
+    static Tunables from_env() {
+        Tunables t;
+        t.no_pack = std::getenv("NSB200_NO_PACK") != nullptr;
+        t.no_resident = std::getenv("NSB200_NO_RESIDENT") != nullptr;
+        t.no_fast = std::getenv("NSB200_NO_FAST") != nullptr;
+        t.explicit_items = std::getenv("NSB200_EXPLICIT_ITEMS") != nullptr;
+        t.trace = std::getenv("NSB200_TRACE") != nullptr;
+        if (const char* s = std::getenv("NSB200_ITEM_POSTINGS")) t.item_postings = std::max(0L, std::atol(s));
+        if (const char* s = std::getenv("NSB200_WINDOW_TILES")) t.window_tiles = std::max(0, std::atoi(s));
+        if (const char* s = std::getenv("NSB200_L2_PREFETCH")) t.l2_prefetch = std::atoi(s) != 0 ? 1 : 0;
+        if (const char* s = std::getenv("NSB200_IMPACT")) t.impact = std::atoi(s) != 0 ? 1 : 0;
+        return t;
+    }
+};
+
 struct SegState {
     uint32_t gseg = 0, ndocs = 0, T = 0, ntiles = 0;
     uint64_t P = 0;
     float avgdl = 0.f;
-    uint2* d_post = nullptr;
+    uint2* d_post = nullptr;   // raw postings; nullptr when the segment keeps only its resident impacts (NS_SEG_DROP_RAW)
     float* d_norm = nullptr;   // per doc (unpacked segments)
     float* d_lut = nullptr;    // per distinct doc length (packed segments)
     bool packed = false;
@@ -98,6 +121,7 @@ struct BatchRes {
     size_t scratch_cap = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_h2d = nullptr;  // the descriptor upload of the batch using this resource set has finished
     ~BatchRes() {
         cudaSetDevice(device);
         if (d_blob) cudaFree(d_blob);
@@ -106,11 +130,24 @@ struct BatchRes {
         if (h_out) cudaFreeHost(h_out);
         for (auto& e : ev)
             if (e) cudaEventDestroy(e);
+        if (ev_h2d) cudaEventDestroy(ev_h2d);
         if (stream) cudaStreamDestroy(stream);
     }
 };
 
 }  // namespace
+
+// What a batch needs from the index handle that created it.  Shared (shared_ptr) so that destroying a batch
+// AFTER its index handle — e.g. garbage-collected wrappers going away in arbitrary order — is harmless.
+struct IndexShared {
+    int device = 0;
+    int sm_count = 148;
+    Tunables tun;
+    std::unordered_map<const void*, int> occupancy;  // kernel variant -> resident CTAs per SM (filled at create)
+    std::mutex mu;                                    // guards pool / closed
+    std::vector<std::unique_ptr<BatchRes>> pool;
+    bool closed = false;
+};
 
 struct ns_index {
     int device = 0;
@@ -118,13 +155,11 @@ struct ns_index {
     std::mutex mu;
     std::shared_ptr<IndexState> live;
     std::vector<SegState> staged;
-    std::vector<std::unique_ptr<BatchRes>> pool;
-    std::unordered_map<const void*, int> occupancy;  // kernel variant -> resident CTAs per SM
-    int sm_count = 148;
+    std::shared_ptr<IndexShared> sh;
 };
 
 struct ns_batch {
-    ns_index* owner = nullptr;
+    std::shared_ptr<IndexShared> owner;
     std::shared_ptr<IndexState> st;
     std::unique_ptr<BatchRes> res;
     uint32_t Q = 0, k = 0;
@@ -142,19 +177,62 @@ struct ns_batch {
     uint32_t* d_dstart = nullptr;
     uint64_t nterms = 0, postings = 0;
     std::vector<uint64_t> weight;  // postings per query (host copy, for re-splitting)
-    // device sub-arrays of the input blob
+    bool needs_raw = false;        // some term is scored from raw postings (per-batch pre-pass or non-impact kernel)
+    // Device blob of one batch:
+    //   [0, up_bytes)                      uploaded per batch: qoff | terms | order (or the explicit item list) | dist | dstart
+    //   [off_zero, off_zero + zero_bytes)  zeroed per launch: queue head | per-query locks | per-query done counts |
+    //                                      published count | result blob (hits | nhits | found)
     uint32_t* d_qoff = nullptr;
     DevTerm* d_terms = nullptr;
-    DevItem* d_items = nullptr;
-    uint32_t* d_list_off = nullptr;
+    DevItem* d_items = nullptr;   // explicit items, or order[] when implicit_items
     uint32_t* d_counter = nullptr;
-    size_t off_items = 0, off_list = 0, off_counter = 0, in_bytes = 0, items_cap = 0;
+    uint32_t* d_qlock = nullptr;
+    uint32_t* d_qdone = nullptr;
+    uint32_t* d_npub = nullptr;
+    size_t off_items = 0, up_bytes = 0, items_cap = 0, off_zero = 0, zero_bytes = 0;
     uint8_t* d_out = nullptr;  // hits | nhits | found, contiguous == h_out layout
     ns_hit* d_out_hits = nullptr;
     uint32_t* d_out_n = nullptr;
     unsigned long long* d_out_found = nullptr;
     size_t out_bytes = 0, off_n = 0, off_found = 0;
     bool launched = false;
+};
+
+// Pinned staging + device posting array of one segment being uploaded (ns_upload_*).
+struct ns_upload {
+    ns_index* owner = nullptr;
+    uint64_t P = 0;
+    uint2* d_post = nullptr;
+    uint8_t* h_pinned = nullptr;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;  // ns_upload_push may be called from the threads that read the barrel files
+};
+
+// Peer exchange of result blobs (see PublishDest in bm25_kernels.cuh).  One per (rank, device).
+struct ns_exchange {
+    int device = 0;
+    uint32_t world = 1, rank = 0, slots = 1, max_q = 0;
+    size_t stride = 0;        // bytes reserved per rank inside a gather region (blob of max_q queries at NS_MAX_K)
+    size_t slot_bytes = 0;    // world * stride
+    size_t off_flags = 0, off_status = 0, off_merged = 0, off_pub = 0, total = 0;
+    uint8_t* d_mem = nullptr; // gather[slots][world][stride] | flags[slots][64] | status[slots] | merged[slots][stride] | PublishDest[slots]
+    struct Dest {
+        uint32_t rank;
+        uint8_t* base;        // the destination's d_mem as mapped into this process / device
+        bool ipc;
+    };
+    std::vector<Dest> dests;
+    bool receiver = false;    // this rank is one of its own destinations: it waits for all ranks and merges
+    uint64_t timeout_ns = 2000000000ull;
+    uint8_t* h_out = nullptr; // pinned, stride + 256 bytes
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_done[8] = {};  // per slot: merge of the last step using the slot has been enqueued
+    std::mutex mu;
+    uint8_t* gather(uint8_t* base, uint32_t slot) const { return base + (size_t)slot * slot_bytes; }
+    uint32_t* flags(uint8_t* base, uint32_t slot) const { return reinterpret_cast<uint32_t*>(base + off_flags + (size_t)slot * 256); }
+    uint32_t* status(uint32_t slot) const { return reinterpret_cast<uint32_t*>(d_mem + off_status + (size_t)slot * 256); }
+    uint8_t* merged(uint32_t slot) const { return d_mem + off_merged + (size_t)slot * stride; }
+    PublishDest* pub(uint32_t slot) const { return reinterpret_cast<PublishDest*>(d_mem + off_pub) + slot; }
 };
 
 extern "C" const char* ns_last_error(void) { return last_error(); }
@@ -164,6 +242,51 @@ extern "C" int ns_device_count(void) {
     if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
     return n;
 }
+
+namespace {
+
+struct KernelCfg {
+    const void* fn;
+    size_t smem;
+    int threads = kThreads;
+};
+
+template <int TDW, int KCAP, bool FAST, bool IMPACT, int NG>
+KernelCfg cfg_of() {
+    return KernelCfg{(const void*)bm25_score_topk_kernel<TDW, KCAP, FAST, IMPACT, NG>,
+                     sizeof(WarpSmem<TDW, KCAP>) * kWarpsPerBlock};
+}
+
+template <int TDW, int KCAP, int NG>
+KernelCfg pick_kernel_tk(bool fast, bool impact) {
+    if (fast) return impact ? cfg_of<TDW, KCAP, true, true, NG>() : cfg_of<TDW, KCAP, true, false, NG>();
+    return impact ? cfg_of<TDW, KCAP, false, true, NG>() : cfg_of<TDW, KCAP, false, false, NG>();
+}
+
+// wide: some (query, segment) has more than 32 terms (two 32-term register groups per lane)
+KernelCfg pick_kernel(uint32_t k, bool fast, bool impact, bool wide) {
+    if (wide) return k <= 16 ? pick_kernel_tk<kTileDocs, 16, 2>(fast, impact) : pick_kernel_tk<kTileDocs, 104, 2>(fast, impact);
+    return k <= 16 ? pick_kernel_tk<kTileDocs, 16, 1>(fast, impact) : pick_kernel_tk<kTileDocs, 104, 1>(fast, impact);
+}
+
+// The dynamic shared-memory opt-in and the occupancy query of every kernel variant, done once per index
+// handle: neither belongs on the launch path (cudaFuncSetAttribute may wait for the device, which must not
+// happen while a peer-exchange wait kernel is spinning).
+int init_kernel_table(IndexShared* idx) {
+    for (int kk = 0; kk < 2; kk++)
+        for (int fast = 0; fast < 2; fast++)
+            for (int impact = 0; impact < 2; impact++)
+                for (int wide = 0; wide < 2; wide++) {
+                    const KernelCfg cfg = pick_kernel(kk ? 100u : 10u, fast != 0, impact != 0, wide != 0);
+                    int per_sm = 0;
+                    NS_CUDA(cudaFuncSetAttribute(cfg.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
+                    NS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cfg.fn, cfg.threads, cfg.smem));
+                    idx->occupancy[cfg.fn] = per_sm;
+                }
+    return NS_OK;
+}
+
+}  // namespace
 
 extern "C" int ns_index_create(int device, ns_index** out) {
     if (!out) { set_error("ns_index_create: out is null"); return NS_ERR_INVALID; }
@@ -179,9 +302,17 @@ extern "C" int ns_index_create(int device, ns_index** out) {
     NS_CUDA(cudaSetDevice(device));
     auto* idx = new ns_index();
     idx->device = device;
+    idx->sh = std::make_shared<IndexShared>();
+    idx->sh->device = device;
+    idx->sh->tun = Tunables::from_env();
     cudaDeviceProp prop;
     NS_CUDA(cudaGetDeviceProperties(&prop, device));
-    idx->sm_count = prop.multiProcessorCount;
+    idx->sh->sm_count = prop.multiProcessorCount;
+    int rc = init_kernel_table(idx->sh.get());
+    if (rc != NS_OK) {
+        delete idx;
+        return rc;
+    }
     *out = idx;
     return NS_OK;
 }
@@ -190,30 +321,34 @@ extern "C" void ns_index_destroy(ns_index* idx) {
     if (!idx) return;
     cudaSetDevice(idx->device);
     for (auto& s : idx->staged) s.release();
-    idx->pool.clear();
+    {
+        std::lock_guard<std::mutex> lk(idx->sh->mu);
+        idx->sh->closed = true;  // batches still alive free their resources themselves
+        idx->sh->pool.clear();
+    }
     idx->live.reset();
     delete idx;
 }
 
-extern "C" int ns_index_add_segment(ns_index* idx, uint32_t global_seg, uint32_t N, float avgdl,
-                                    const uint32_t* doc_len, uint32_t T, const uint64_t* term_begin,
-                                    const uint32_t* term_count, const void* postings, uint64_t P) {
-    if (!idx || (N && !doc_len) || (T && (!term_begin || !term_count)) || (P && !postings)) {
-        set_error("ns_index_add_segment: null argument");
-        return NS_ERR_INVALID;
-    }
-    if (P >= 0xFFFFFFFFull) { set_error("segment has >= 2^32 postings; split it"); return NS_ERR_INVALID; }
-    if (global_seg >= 0x80000000u) { set_error("ns_index_add_segment: global_seg must be < 2^31"); return NS_ERR_INVALID; }
+namespace {
+
+// Everything after the raw postings are on the device: validate, tile table, doc-length factors, packing,
+// resident impacts; stages the segment on success.  Takes ownership of d_post (freed on failure).
+int add_segment_core(ns_index* idx, uint32_t global_seg, uint32_t N, float avgdl, const uint32_t* doc_len, uint32_t T,
+                     const uint64_t* term_begin, const uint32_t* term_count, const float* row_idf, uint2* d_post,
+                     uint64_t P, uint32_t flags) {
+    SegState s;
+    s.d_post = d_post;
     std::vector<uint32_t> begin32(T);
     for (uint32_t t = 0; t < T; t++) {
-        if (term_begin[t] + term_count[t] > P) {
+        // overflow-safe form of begin + count <= P
+        if ((uint64_t)term_count[t] > P || term_begin[t] > P - (uint64_t)term_count[t]) {
+            s.release();
             set_error("ns_index_add_segment: row " + std::to_string(t) + " exceeds the posting array");
             return NS_ERR_FORMAT;
         }
         begin32[t] = (uint32_t)term_begin[t];
     }
-    NS_CUDA(cudaSetDevice(idx->device));
-    SegState s;
     s.gseg = global_seg;
     s.ndocs = N;
     s.T = T;
@@ -229,7 +364,7 @@ extern "C" int ns_index_add_segment(ns_index* idx, uint32_t global_seg, uint32_t
     std::vector<uint32_t> uniq(doc_len, doc_len + N);
     std::sort(uniq.begin(), uniq.end());
     uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
-    bool can_pack = uniq.size() <= 65536 && !std::getenv("NSB200_NO_PACK");
+    bool can_pack = uniq.size() <= 65536 && !idx->sh->tun.no_pack;
     std::vector<unsigned short> code;
     if (can_pack) {
         code.resize(N);
@@ -239,12 +374,14 @@ extern "C" int ns_index_add_segment(ns_index* idx, uint32_t global_seg, uint32_t
 
     uint32_t *d_len = nullptr, *d_begin = nullptr, *d_count = nullptr;
     unsigned short* d_code = nullptr;
+    float* d_idf = nullptr;
     unsigned int* d_err = nullptr;  // [0] posting-order violations, [1] norms outside the fast-division range, [2] tf > 0xFFFF
     auto cleanup = [&]() {
         if (d_len) cudaFree(d_len);
         if (d_begin) cudaFree(d_begin);
         if (d_count) cudaFree(d_count);
         if (d_code) cudaFree(d_code);
+        if (d_idf) cudaFree(d_idf);
         if (d_err) cudaFree(d_err);
     };
 #define NS_CUDA_SEG(expr)                                                                       \
@@ -260,27 +397,34 @@ extern "C" int ns_index_add_segment(ns_index* idx, uint32_t global_seg, uint32_t
 
     const size_t tile_entries = (size_t)T * (s.ntiles + 1);
     const size_t nlen = can_pack ? uniq.size() : (size_t)N;  // lengths the norm kernel evaluates
-    NS_CUDA_SEG(cudaMalloc(&s.d_post, (P + 2) * sizeof(uint2)));  // +2: bulk copies round slices up to 16 B
     NS_CUDA_SEG(cudaMalloc(&s.d_tileoff, std::max<size_t>(16, tile_entries * sizeof(uint32_t))));
     NS_CUDA_SEG(cudaMalloc(&d_len, std::max<size_t>(16, nlen * 4)));
     NS_CUDA_SEG(cudaMalloc(&d_begin, std::max<size_t>(16, (size_t)T * 4)));
     NS_CUDA_SEG(cudaMalloc(&d_count, std::max<size_t>(16, (size_t)T * 4)));
     NS_CUDA_SEG(cudaMalloc(&d_err, 3 * sizeof(unsigned int)));
     NS_CUDA_SEG(cudaMemset(d_err, 0, 3 * sizeof(unsigned int)));
-    if (P) NS_CUDA_SEG(cudaMemcpy(s.d_post, postings, P * sizeof(uint2), cudaMemcpyHostToDevice));
+    unsigned int h_errs[3] = {0, 0, 0};
     if (T) {
         NS_CUDA_SEG(cudaMemcpy(d_begin, begin32.data(), (size_t)T * 4, cudaMemcpyHostToDevice));
         NS_CUDA_SEG(cudaMemcpy(d_count, term_count, (size_t)T * 4, cudaMemcpyHostToDevice));
-        const int blocks = (int)std::min<uint64_t>(((uint64_t)T + 7) / 8, (uint64_t)idx->sm_count * 32);
+        const int blocks = (int)std::min<uint64_t>(((uint64_t)T + 7) / 8, (uint64_t)idx->sh->sm_count * 32);
         validate_rows_kernel<<<blocks, 256>>>(s.d_post, d_begin, d_count, T, N, d_err);
         NS_CUDA_SEG(cudaGetLastError());
+        NS_CUDA_SEG(cudaMemcpy(h_errs, d_err, sizeof(h_errs), cudaMemcpyDeviceToHost));
+        // Reject BEFORE any kernel indexes a per-doc array with a posting's docId: every later kernel
+        // (tile table, packing, impacts) relies on docId < N and sorted rows.
+        if (h_errs[0]) {
+            cleanup();
+            s.release();
+            set_error("segment " + std::to_string(global_seg) + ": " + std::to_string(h_errs[0]) +
+                      " postings are out of order, duplicated or have docId >= N");
+            return NS_ERR_FORMAT;
+        }
         const uint64_t tb = (tile_entries + 255) / 256;
-        tile_table_kernel<<<(int)std::min<uint64_t>(tb, (uint64_t)idx->sm_count * 64), 256>>>(
+        tile_table_kernel<<<(int)std::min<uint64_t>(tb, (uint64_t)idx->sh->sm_count * 64), 256>>>(
             s.d_post, d_begin, d_count, T, s.ntiles, idx->tile_docs, s.d_tileoff);
         NS_CUDA_SEG(cudaGetLastError());
     }
-    unsigned int h_errs[3] = {0, 0, 0};
-    NS_CUDA_SEG(cudaMemcpy(h_errs, d_err, sizeof(h_errs), cudaMemcpyDeviceToHost));
     if (h_errs[2]) can_pack = false;
     float* d_normdst = nullptr;
     if (can_pack) {
@@ -305,52 +449,42 @@ extern "C" int ns_index_add_segment(ns_index* idx, uint32_t global_seg, uint32_t
     if (can_pack && P) {
         NS_CUDA_SEG(cudaMalloc(&d_code, std::max<size_t>(16, (size_t)N * 2)));
         NS_CUDA_SEG(cudaMemcpy(d_code, code.data(), (size_t)N * 2, cudaMemcpyHostToDevice));
-        pack_postings_kernel<<<idx->sm_count * 16, 256>>>(s.d_post, P, d_code);
+        pack_postings_kernel<<<idx->sh->sm_count * 16, 256>>>(s.d_post, P, d_code, N);
         NS_CUDA_SEG(cudaGetLastError());
     }
     s.packed = can_pack;
-    // Resident impacts: the term score of every posting under the row's own idf (src/api_engine.cpp:45-47
-    // with df = LexEntry.count, which is what every writer stores: include/segment_writer.hpp:147-149).
-    // A query term whose idf differs bit-wise from this one goes through the per-batch pre-pass instead.
-    float* d_idf = nullptr;
-    if (P && T && !std::getenv("NSB200_NO_RESIDENT")) {
+    // Resident impacts: the term score of every posting under the row's idf — the caller's row_idf[]
+    // (the engine passes bm25_idf(N, df) of its lexicon) or bm25_idf(N, count) (src/api_engine.cpp:45-47 with
+    // df = LexEntry.count, what every writer stores: include/segment_writer.hpp:147-149).  A query term whose
+    // idf differs bit-wise from the row's goes through the per-batch pre-pass, which needs the raw postings.
+    const bool drop_raw = (flags & NS_SEG_DROP_RAW) != 0u;
+    if (P && T && !idx->sh->tun.no_resident) {
         std::vector<float> h_idf(T);
         s.h_idf_bits.resize(T);
         for (uint32_t t = 0; t < T; t++) {
-            h_idf[t] = bm25_idf(N, term_count[t]);
+            h_idf[t] = row_idf ? row_idf[t] : bm25_idf(N, term_count[t]);
             std::memcpy(&s.h_idf_bits[t], &h_idf[t], 4);
         }
-        cudaError_t e1 = cudaMalloc(&d_idf, (size_t)T * 4);
-        if (e1 == cudaSuccess) e1 = cudaMalloc(&s.d_imp, (P + 2) * sizeof(uint2));
-        if (e1 == cudaSuccess) e1 = cudaMemcpy(d_idf, h_idf.data(), (size_t)T * 4, cudaMemcpyHostToDevice);
-        if (e1 == cudaSuccess) {
-            const int blocks = (int)std::min<uint64_t>(((uint64_t)T + 7) / 8, (uint64_t)idx->sm_count * 32);
-            build_impacts_kernel<<<blocks, 256>>>(s.d_post, d_begin, d_count, d_idf, T, d_normdst, can_pack ? 1u : 0u,
-                                                  kK1 + 1.0f, s.d_imp);
-            e1 = cudaGetLastError();
-            if (e1 == cudaSuccess) e1 = cudaDeviceSynchronize();
+        NS_CUDA_SEG(cudaMalloc(&d_idf, (size_t)T * 4));
+        NS_CUDA_SEG(cudaMemcpy(d_idf, h_idf.data(), (size_t)T * 4, cudaMemcpyHostToDevice));
+        if (drop_raw) {
+            s.d_imp = s.d_post;  // in place: the raw payload of every row-covered posting is replaced by its score
+            s.d_post = nullptr;
+        } else {
+            NS_CUDA_SEG(cudaMalloc(&s.d_imp, (P + 2) * sizeof(uint2)));
         }
-        if (d_idf) cudaFree(d_idf);
-        if (e1 != cudaSuccess) {
-            set_error(std::string("CUDA error building resident impacts: ") + cudaGetErrorString(e1));
-            cleanup();
-            s.release();
-            return NS_ERR_CUDA;
-        }
+        const int blocks = (int)std::min<uint64_t>(((uint64_t)T + 7) / 8, (uint64_t)idx->sh->sm_count * 32);
+        build_impacts_kernel<<<blocks, 256>>>(drop_raw ? s.d_imp : s.d_post, d_begin, d_count, d_idf, T, d_normdst,
+                                              can_pack ? 1u : 0u, kK1 + 1.0f, s.d_imp);
+        NS_CUDA_SEG(cudaGetLastError());
     }
-    NS_CUDA_SEG(cudaMemcpy(h_errs, d_err, sizeof(h_errs), cudaMemcpyDeviceToHost));
     NS_CUDA_SEG(cudaDeviceSynchronize());
-    const unsigned int h_err = h_errs[0];
+    NS_CUDA_SEG(cudaMemcpy(h_errs, d_err, sizeof(h_errs), cudaMemcpyDeviceToHost));
     s.norm_in_range = (h_errs[1] == 0);
     cleanup();
 #undef NS_CUDA_SEG
-    if (h_err) {
-        s.release();
-        set_error("segment " + std::to_string(global_seg) + ": " + std::to_string(h_err) +
-                  " postings are out of order, duplicated or have docId >= N");
-        return NS_ERR_FORMAT;
-    }
-    s.bytes = (s.d_imp ? 2 : 1) * P * sizeof(uint2) + (can_pack ? (uint64_t)uniq.size() * 4 : (uint64_t)N * 4) + tile_entries * 4;
+    s.bytes = ((s.d_imp ? 1 : 0) + (s.d_post ? 1 : 0)) * P * sizeof(uint2) +
+              (can_pack ? (uint64_t)uniq.size() * 4 : (uint64_t)N * 4) + tile_entries * 4;
     std::lock_guard<std::mutex> lk(idx->mu);
     for (auto& o : idx->staged) {
         if (o.gseg == global_seg) {
@@ -361,6 +495,115 @@ extern "C" int ns_index_add_segment(ns_index* idx, uint32_t global_seg, uint32_t
     }
     idx->staged.push_back(std::move(s));
     return NS_OK;
+}
+
+int check_segment_args(ns_index* idx, uint32_t global_seg, uint32_t N, const uint32_t* doc_len, uint32_t T,
+                       const uint64_t* term_begin, const uint32_t* term_count, uint64_t P) {
+    if (!idx || (N && !doc_len) || (T && (!term_begin || !term_count))) {
+        set_error("ns_index_add_segment: null argument");
+        return NS_ERR_INVALID;
+    }
+    if (P >= 0xFFFFFFFFull) { set_error("segment has >= 2^32 postings; split it"); return NS_ERR_INVALID; }
+    if (global_seg >= 0x80000000u) { set_error("ns_index_add_segment: global_seg must be < 2^31"); return NS_ERR_INVALID; }
+    return NS_OK;
+}
+
+}  // namespace
+
+extern "C" int ns_index_add_segment_ex(ns_index* idx, uint32_t global_seg, uint32_t N, float avgdl,
+                                       const uint32_t* doc_len, uint32_t T, const uint64_t* term_begin,
+                                       const uint32_t* term_count, const float* row_idf, const void* postings,
+                                       uint64_t P, uint32_t flags) {
+    int rc = check_segment_args(idx, global_seg, N, doc_len, T, term_begin, term_count, P);
+    if (rc != NS_OK) return rc;
+    if (P && !postings) { set_error("ns_index_add_segment: null argument"); return NS_ERR_INVALID; }
+    NS_CUDA(cudaSetDevice(idx->device));
+    uint2* d_post = nullptr;
+    NS_CUDA(cudaMalloc(&d_post, (P + 2) * sizeof(uint2)));  // +2: bulk prefetches round slices up to 16 B
+    if (P) {
+        cudaError_t e = cudaMemcpy(d_post, postings, P * sizeof(uint2), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            cudaFree(d_post);
+            set_error(std::string("CUDA error uploading postings: ") + cudaGetErrorString(e));
+            return NS_ERR_CUDA;
+        }
+    }
+    return add_segment_core(idx, global_seg, N, avgdl, doc_len, T, term_begin, term_count, row_idf, d_post, P, flags);
+}
+
+extern "C" int ns_index_add_segment(ns_index* idx, uint32_t global_seg, uint32_t N, float avgdl,
+                                    const uint32_t* doc_len, uint32_t T, const uint64_t* term_begin,
+                                    const uint32_t* term_count, const void* postings, uint64_t P) {
+    return ns_index_add_segment_ex(idx, global_seg, N, avgdl, doc_len, T, term_begin, term_count, nullptr, postings, P, 0u);
+}
+
+// ---- streamed upload: the loader reads barrel files straight into pinned memory and pushes every
+// ---- finished range; the copies overlap the remaining file reads ----
+
+extern "C" int ns_upload_begin(ns_index* idx, uint64_t P, ns_upload** out) {
+    if (!idx || !out) { set_error("ns_upload_begin: null argument"); return NS_ERR_INVALID; }
+    *out = nullptr;
+    if (P >= 0xFFFFFFFFull) { set_error("segment has >= 2^32 postings; split it"); return NS_ERR_INVALID; }
+    NS_CUDA(cudaSetDevice(idx->device));
+    auto u = std::make_unique<ns_upload>();
+    u->owner = idx;
+    u->P = P;
+    cudaError_t e = cudaMalloc(&u->d_post, (P + 2) * sizeof(uint2));
+    if (e == cudaSuccess) e = cudaHostAlloc(&u->h_pinned, std::max<size_t>(16, P * sizeof(uint2)), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&u->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        if (u->d_post) cudaFree(u->d_post);
+        if (u->h_pinned) cudaFreeHost(u->h_pinned);
+        set_error(std::string("ns_upload_begin: ") + cudaGetErrorString(e));
+        return NS_ERR_CUDA;
+    }
+    *out = u.release();
+    return NS_OK;
+}
+
+extern "C" void* ns_upload_buffer(ns_upload* u) { return u ? u->h_pinned : nullptr; }
+
+extern "C" int ns_upload_push(ns_upload* u, uint64_t first, uint64_t count) {
+    if (!u || first > u->P || count > u->P - first) { set_error("ns_upload_push: range outside the segment"); return NS_ERR_INVALID; }
+    if (count == 0) return NS_OK;
+    std::lock_guard<std::mutex> lk(u->mu);
+    NS_CUDA(cudaSetDevice(u->owner->device));
+    NS_CUDA(cudaMemcpyAsync(u->d_post + first, u->h_pinned + first * sizeof(uint2), count * sizeof(uint2),
+                            cudaMemcpyHostToDevice, u->stream));
+    return NS_OK;
+}
+
+extern "C" void ns_upload_abort(ns_upload* u) {
+    if (!u) return;
+    cudaSetDevice(u->owner->device);
+    if (u->stream) {
+        cudaStreamSynchronize(u->stream);
+        cudaStreamDestroy(u->stream);
+    }
+    if (u->d_post) cudaFree(u->d_post);
+    if (u->h_pinned) cudaFreeHost(u->h_pinned);
+    delete u;
+}
+
+extern "C" int ns_upload_finish(ns_upload* u, uint32_t global_seg, uint32_t N, float avgdl, const uint32_t* doc_len,
+                                uint32_t T, const uint64_t* term_begin, const uint32_t* term_count,
+                                const float* row_idf, uint32_t flags) {
+    if (!u) { set_error("ns_upload_finish: null"); return NS_ERR_INVALID; }
+    ns_index* idx = u->owner;
+    int rc = check_segment_args(idx, global_seg, N, doc_len, T, term_begin, term_count, u->P);
+    if (rc != NS_OK) { ns_upload_abort(u); return rc; }
+    cudaSetDevice(idx->device);
+    cudaError_t e = cudaStreamSynchronize(u->stream);
+    uint2* d_post = u->d_post;
+    const uint64_t P = u->P;
+    u->d_post = nullptr;
+    ns_upload_abort(u);  // frees the staging, not the device array
+    if (e != cudaSuccess) {
+        cudaFree(d_post);
+        set_error(std::string("ns_upload_finish: ") + cudaGetErrorString(e));
+        return NS_ERR_CUDA;
+    }
+    return add_segment_core(idx, global_seg, N, avgdl, doc_len, T, term_begin, term_count, row_idf, d_post, P, flags);
 }
 
 extern "C" int ns_index_abort(ns_index* idx) {
@@ -431,11 +674,17 @@ extern "C" uint64_t ns_index_device_bytes(const ns_index* idx) {
     return m->live ? m->live->bytes : 0;
 }
 
+std::shared_ptr<const void> nsb::index_live_state(ns_index* idx) {
+    if (!idx) return nullptr;
+    std::lock_guard<std::mutex> lk(idx->mu);
+    return std::static_pointer_cast<const void>(idx->live);
+}
+
 // ---------------------------------------------------------------------------------------------
 
 namespace {
 
-int acquire_res(ns_index* idx, size_t d_need, size_t in_need, size_t out_need, std::unique_ptr<BatchRes>& out) {
+int acquire_res(IndexShared* idx, size_t d_need, size_t in_need, size_t out_need, std::unique_ptr<BatchRes>& out) {
     {
         std::lock_guard<std::mutex> lk(idx->mu);
         for (size_t i = 0; i < idx->pool.size(); i++) {
@@ -459,34 +708,31 @@ int acquire_res(ns_index* idx, size_t d_need, size_t in_need, size_t out_need, s
     NS_CUDA(cudaMallocHost(&r->h_out, r->h_out_cap));
     NS_CUDA(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
     for (auto& e : r->ev) NS_CUDA(cudaEventCreate(&e));
+    NS_CUDA(cudaEventCreateWithFlags(&r->ev_h2d, cudaEventDisableTiming));
     out = std::move(r);
     return NS_OK;
 }
 
 constexpr uint32_t kMaxSplit = 64;
 
-// Cut queries into items of roughly `target` postings (at most kMaxSplit per query, never more
-// than the tile count), order items heaviest first, write items + list_off into the pinned input
-// blob.  forced > 0 gives every query exactly min(forced, tiles) items (tests).
-void build_items(ns_batch* b, uint32_t forced) {
+// Cut queries into items — (query, window of consecutive tiles) — and write what the kernel needs into the
+// pinned input blob at off_items.  Normal case: window-major order with the SAME number of windows for
+// every query, so only the query order[] is written and the kernel derives item i = (order[i % Q], i / Q).
+// forced > 0 (tests) gives every query exactly min(forced, tiles) items, written as an explicit list.
+// Returns the number of bytes written at off_items.
+size_t build_items(ns_batch* b, uint32_t forced) {
     const IndexState& st = *b->st;
+    const Tunables& tun = b->owner->tun;
     const uint32_t Q = b->Q;
     const uint32_t tiles = std::max<uint32_t>(1, st.total_tiles);
-    uint64_t target = 32768;
-    if (const char* s = std::getenv("NSB200_ITEM_POSTINGS")) {
-        long v = std::atol(s);
-        if (v > 0) target = (uint64_t)v;
-    }
+    uint64_t target = tun.item_postings > 0 ? (uint64_t)tun.item_postings : 32768;
     // small batches: cut finer so that every resident warp has work
     const uint64_t want_items = (uint64_t)b->owner->sm_count * 24 * 2;
     if (Q > 0 && b->postings / target + Q < want_items) target = std::max<uint64_t>(1024, b->postings / want_items);
-    // NSB200_WINDOW_TILES=w: tile-major order — every query is cut into windows of ~w tiles and
-    // items are ordered by window first, so that all resident warps sweep the same doc range of
-    // the index at the same time and the hot posting slices are served from L2.
-    uint32_t window = 24;  // tiles per item (set below from the batch shape); 0 = query-major
     // Items per query: ~10 items per resident warp over the whole batch, at least tiles/24 (windows of
     // <= 24 tiles keep the batch's hot slices in L2), at most tiles/4 — and at most 16 for small batches,
     // where all items of a query run at the same time and serialise on the query's result-list lock.
+    uint32_t window;
     {
         const uint64_t warps = (uint64_t)b->owner->sm_count * 24;
         uint64_t ns = warps * 10 / std::max<uint32_t>(1, Q);
@@ -496,84 +742,55 @@ void build_items(ns_batch* b, uint32_t forced) {
         ns = std::max<uint64_t>(1, ns);
         window = (uint32_t)((tiles + ns - 1) / ns);
     }
-    if (const char* s = std::getenv("NSB200_WINDOW_TILES")) window = (uint32_t)std::max(0, std::atoi(s));
+    if (tun.window_tiles >= 0) window = (uint32_t)tun.window_tiles;  // 0 = query-major
     std::vector<uint32_t> nsplit(Q);
-    std::vector<uint32_t> list_off((size_t)Q + 1, 0);
     uint32_t maxs = 1;
+    uint64_t nitems = 0;
     for (uint32_t q = 0; q < Q; q++) {
         uint64_t ns = forced ? forced : (b->weight[q] + target - 1) / target;
         if (!forced && window) ns = (tiles + window - 1) / window;
         ns = std::max<uint64_t>(1, std::min<uint64_t>(ns, std::min<uint64_t>(tiles, kMaxSplit)));
         nsplit[q] = (uint32_t)ns;
         maxs = std::max(maxs, nsplit[q]);
-        list_off[q + 1] = list_off[q] + nsplit[q];
+        nitems += ns;
     }
-    const uint32_t nitems = list_off[Q];
-    // Order: window-major (split asc), heaviest item first inside a window; query-major mode orders
-    // by item weight only.  Sorting the Q queries once replaces a sort over all Q x nsplit items.
+    // Heaviest queries first inside a window (query-major mode: heaviest items first).
     std::vector<uint32_t> order(Q);
     std::iota(order.begin(), order.end(), 0u);
     std::vector<uint64_t> iw(Q);
     for (uint32_t q = 0; q < Q; q++) iw[q] = b->weight[q] / nsplit[q];
     std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return iw[x] > iw[y]; });
-    DevItem* h_items = reinterpret_cast<DevItem*>(b->res->h_in + b->off_items);
+    uint8_t* dst = b->res->h_in + b->off_items;
     b->window_major = window && !forced;
-    static const bool explicit_items = std::getenv("NSB200_EXPLICIT_ITEMS") != nullptr;
-    b->implicit_items = b->window_major && !explicit_items;
+    b->implicit_items = b->window_major && !tun.explicit_items;
     b->nsplit_all = maxs;
+    b->nitems = (uint32_t)nitems;
+    b->max_split = maxs;
     if (b->implicit_items) {
-        // every query has the same number of windows: item i = (order[i % Q], window i / Q); only order[] is uploaded
-        std::memcpy(h_items, order.data(), (size_t)Q * 4);
-    } else if (window && !forced) {
-        size_t at = 0;
+        if (Q) std::memcpy(dst, order.data(), (size_t)Q * 4);
+        return (size_t)Q * 4;
+    }
+    DevItem* h_items = reinterpret_cast<DevItem*>(dst);
+    size_t at = 0;
+    if (b->window_major) {
         for (uint32_t sp = 0; sp < maxs; sp++)
             for (uint32_t q : order)
                 if (sp < nsplit[q]) h_items[at++] = DevItem{q, (sp << 16) | nsplit[q]};
     } else {
-        size_t at = 0;
         for (uint32_t q : order)
             for (uint32_t sp = 0; sp < nsplit[q]; sp++) h_items[at++] = DevItem{q, (sp << 16) | nsplit[q]};
     }
-    std::memcpy(b->res->h_in + b->off_list, list_off.data(), ((size_t)Q + 1) * 4);
-    b->nitems = nitems;
-    b->max_split = maxs;
-}
-
-struct KernelCfg {
-    const void* fn;
-    size_t smem;
-    int threads = kThreads;
-};
-
-template <int TDW, int KCAP, bool FAST, bool IMPACT, int NG>
-KernelCfg cfg_of() {
-    return KernelCfg{(const void*)bm25_score_topk_kernel<TDW, KCAP, FAST, IMPACT, NG>,
-                     sizeof(WarpSmem<TDW, KCAP>) * kWarpsPerBlock};
-}
-
-template <int TDW, int KCAP, int NG>
-KernelCfg pick_kernel_tk(bool fast, bool impact) {
-    if (fast) return impact ? cfg_of<TDW, KCAP, true, true, NG>() : cfg_of<TDW, KCAP, true, false, NG>();
-    return impact ? cfg_of<TDW, KCAP, false, true, NG>() : cfg_of<TDW, KCAP, false, false, NG>();
-}
-
-// wide: some (query, segment) has more than 32 terms (two 32-term register groups per lane)
-KernelCfg pick_kernel(uint32_t k, bool fast, bool impact, bool wide) {
-    if (wide) return k <= 16 ? pick_kernel_tk<kTileDocs, 16, 2>(fast, impact) : pick_kernel_tk<kTileDocs, 104, 2>(fast, impact);
-    return k <= 16 ? pick_kernel_tk<kTileDocs, 16, 1>(fast, impact) : pick_kernel_tk<kTileDocs, 104, 1>(fast, impact);
+    return at * sizeof(DevItem);
 }
 
 }  // namespace
 
-extern "C" int ns_batch_prepare(ns_index* idx, uint32_t Q, int k_in, const uint64_t* q_off, const ns_qterm* terms,
-                                ns_batch** out) {
+int nsb::batch_prepare_on(ns_index* idx, const std::shared_ptr<const void>& state, uint32_t Q, int k_in,
+                          const uint64_t* q_off, const ns_qterm* terms, ns_batch** out) {
     if (!idx || !out || !q_off || (Q && q_off[Q] && !terms)) { set_error("ns_batch_prepare: null argument"); return NS_ERR_INVALID; }
     *out = nullptr;
-    std::shared_ptr<IndexState> st;
-    {
-        std::lock_guard<std::mutex> lk(idx->mu);
-        st = idx->live;
-    }
+    std::shared_ptr<IndexState> st =
+        std::const_pointer_cast<IndexState>(std::static_pointer_cast<const IndexState>(state));
     if (!st) { set_error("ns_batch_prepare: index has no committed segments"); return NS_ERR_STATE; }
     NS_CUDA(cudaSetDevice(idx->device));
     const uint32_t k = (uint32_t)std::max(1, std::min(k_in, NS_MAX_K));  // src/api_engine.cpp:377
@@ -590,8 +807,7 @@ extern "C" int ns_batch_prepare(ns_index* idx, uint32_t Q, int k_in, const uint6
     struct DistHash {
         size_t operator()(const DistKey& k) const { return (size_t)(k.slot_row * 0x9E3779B97F4A7C15ull ^ k.idf_bits); }
     };
-    std::unordered_map<DistKey, uint32_t, DistHash> dist_of;
-    dist_of.reserve(nin);
+    std::unordered_map<DistKey, uint32_t, DistHash> dist_of;  // only touched by terms whose scores are not resident
     std::vector<DevDistinct> dist;
     std::vector<uint32_t> dstart;
     uint64_t dist_post = 0;
@@ -602,7 +818,11 @@ extern "C" int ns_batch_prepare(ns_index* idx, uint32_t Q, int k_in, const uint6
     uint32_t max_in_seg = 0;
     bool scan_always = false;
     bool fast = true;
-    for (auto& sg : st->segs) fast = fast && sg.norm_in_range;
+    bool all_raw = true;
+    for (auto& sg : st->segs) {
+        fast = fast && sg.norm_in_range;
+        all_raw = all_raw && (sg.d_post != nullptr || sg.P == 0);
+    }
     uint32_t memo_seg = 0xFFFFFFFFu;
     int64_t memo_slot = -1;
     {
@@ -620,7 +840,7 @@ extern "C" int ns_batch_prepare(ns_index* idx, uint32_t Q, int k_in, const uint6
                 memo_seg = t.seg;
                 memo_slot = it == st->slot_of.end() ? -1 : (int64_t)it->second;
             }
-            if (memo_slot < 0) continue;  // another rank's segment
+            if (memo_slot < 0) continue;  // another device's / rank's segment
             const uint32_t slot = (uint32_t)memo_slot;
             const SegState& sg = st->segs[slot];
             if (t.row >= sg.T) { set_error("ns_batch_prepare: row out of range"); return NS_ERR_INVALID; }
@@ -644,6 +864,11 @@ extern "C" int ns_batch_prepare(ns_index* idx, uint32_t Q, int k_in, const uint6
                 n_resident++;
                 continue;
             }
+            if (!sg.d_post) {
+                set_error("ns_batch_prepare: a term's idf differs from the one its segment's resident scores were built with, "
+                          "and the segment was uploaded without raw postings (NS_SEG_DROP_RAW)");
+                return NS_ERR_STATE;
+            }
             // distinct (segment, row, idf): one evaluation of the term's scores per batch
             nonres_post += cnt;
             const DistKey key{((uint64_t)slot << 32) | t.row, idf_bits};
@@ -663,7 +888,7 @@ extern "C" int ns_batch_prepare(ns_index* idx, uint32_t Q, int k_in, const uint6
         total_post += b->weight[q];
     }
 
-    b->owner = idx;
+    b->owner = idx->sh;
     b->st = st;
     b->Q = Q;
     b->k = k;
@@ -677,45 +902,45 @@ extern "C" int ns_batch_prepare(ns_index* idx, uint32_t Q, int k_in, const uint6
     b->dist_postings = dist_post;
     // Share term scores across the batch when that removes enough evaluations: the pre-pass reads
     // and writes every distinct posting once, the scoring kernel then skips ~2/3 of its arithmetic.
+    // Segments without raw postings can only be scored from impacts.
     {
-        static const char* env = std::getenv("NSB200_IMPACT");
         const double share = dist_post ? (double)nonres_post / (double)dist_post : 0.0;
-        b->impact = n_resident > 0 || (env ? (std::atoi(env) != 0 && dist_post > 0) : (share >= 1.5));
+        const int env = idx->sh->tun.impact;
+        b->impact = !all_raw || n_resident > 0 || (env >= 0 ? (env != 0 && dist_post > 0) : (share >= 1.5));
     }
 
     const size_t tiles = std::max<uint32_t>(1, st->total_tiles);
     b->items_cap = (size_t)Q * std::min<size_t>(tiles, kMaxSplit);
     const size_t sz_qoff = align_up(((size_t)Q + 1) * 4);
     const size_t sz_terms = align_up(std::max<size_t>(1, kept.size()) * sizeof(DevTerm));
-    const size_t sz_items = align_up(std::max<size_t>(1, b->items_cap) * sizeof(DevItem));
-    const size_t sz_list = align_up(((size_t)Q + 1) * 4);
-    const size_t sz_counter = align_up(4 + (size_t)Q * 4);  // work-queue head + per-query locks, zeroed per launch
     const size_t sz_dist = align_up(std::max<size_t>(1, dist.size()) * sizeof(DevDistinct));
     const size_t sz_dstart = align_up(dstart.size() * 4);
-    b->off_items = sz_qoff + sz_terms;
-    b->off_list = b->off_items + sz_items;
-    b->off_counter = b->off_list + sz_list;
-    const size_t off_dist = b->off_counter + sz_counter;
+    const size_t sz_items = align_up(std::max<size_t>(1, b->items_cap) * sizeof(DevItem));
+    const size_t off_dist = sz_qoff + sz_terms;
     const size_t off_dstart = off_dist + sz_dist;
-    b->in_bytes = off_dstart + sz_dstart;
+    b->off_items = off_dstart + sz_dstart;  // last uploaded region: only its used prefix is copied
+    const size_t in_cap = b->off_items + sz_items;
+    // zeroed per launch: queue head | locks[Q] | done[Q] | published | result blob
+    const size_t sz_ctrl = align_up((2 + 2 * (size_t)Q) * 4);
     const size_t sz_hits = align_up(std::max<size_t>(1, (size_t)Q * k) * sizeof(ns_hit));
     const size_t sz_n = align_up(std::max<size_t>(1, Q) * 4);
     const size_t sz_found = align_up(std::max<size_t>(1, Q) * 8);
     b->out_bytes = sz_hits + sz_n + sz_found;
     b->off_n = sz_hits;
     b->off_found = sz_hits + sz_n;
+    b->off_zero = in_cap;
+    b->zero_bytes = sz_ctrl + b->out_bytes;
 
-    int rc = acquire_res(idx, b->in_bytes + b->out_bytes, b->in_bytes, b->out_bytes, b->res);
+    int rc = acquire_res(idx->sh.get(), in_cap + b->zero_bytes, in_cap, b->out_bytes, b->res);
     if (rc != NS_OK) return rc;
     BatchRes& r = *b->res;
     std::memcpy(r.h_in, qoff32.data(), ((size_t)Q + 1) * 4);
     if (!kept.empty()) std::memcpy(r.h_in + sz_qoff, kept.data(), kept.size() * sizeof(DevTerm));
-    std::memset(r.h_in + b->off_counter, 0, 4 + (size_t)Q * 4);
     if (!dist.empty()) std::memcpy(r.h_in + off_dist, dist.data(), dist.size() * sizeof(DevDistinct));
     std::memcpy(r.h_in + off_dstart, dstart.data(), dstart.size() * 4);
     b->d_dist = reinterpret_cast<DevDistinct*>(r.d_blob + off_dist);
     b->d_dstart = reinterpret_cast<uint32_t*>(r.d_blob + off_dstart);
-    if (b->impact) {
+    if (b->impact && dist_post) {
         const size_t need = (dist_post + 4) * sizeof(uint2);
         if (r.scratch_cap < need) {
             if (r.d_scratch) cudaFree(r.d_scratch);
@@ -727,43 +952,53 @@ extern "C" int ns_batch_prepare(ns_index* idx, uint32_t Q, int k_in, const uint6
             r.scratch_cap = cap;
         }
     }
-    build_items(b.get(), 0);
+    const size_t items_bytes = build_items(b.get(), 0);
+    b->up_bytes = b->off_items + items_bytes;
     b->d_qoff = reinterpret_cast<uint32_t*>(r.d_blob);
     b->d_terms = reinterpret_cast<DevTerm*>(r.d_blob + sz_qoff);
     b->d_items = reinterpret_cast<DevItem*>(r.d_blob + b->off_items);
-    b->d_list_off = reinterpret_cast<uint32_t*>(r.d_blob + b->off_list);
-    b->d_counter = reinterpret_cast<uint32_t*>(r.d_blob + b->off_counter);
-    b->d_out = r.d_blob + b->in_bytes;
+    uint32_t* ctrl = reinterpret_cast<uint32_t*>(r.d_blob + b->off_zero);
+    b->d_counter = ctrl;
+    b->d_npub = ctrl + 1;
+    b->d_qlock = ctrl + 2;
+    b->d_qdone = ctrl + 2 + Q;
+    b->d_out = r.d_blob + b->off_zero + sz_ctrl;
     b->d_out_hits = reinterpret_cast<ns_hit*>(b->d_out);
     b->d_out_n = reinterpret_cast<uint32_t*>(b->d_out + b->off_n);
     b->d_out_found = reinterpret_cast<unsigned long long*>(b->d_out + b->off_found);
-    NS_CUDA(cudaMemcpyAsync(r.d_blob, r.h_in, b->in_bytes, cudaMemcpyHostToDevice, r.stream));
-    NS_CUDA(cudaStreamSynchronize(r.stream));
+    // The upload is NOT waited for here: launches on any stream order themselves after ev_h2d, so the
+    // caller's host thread goes on (to the launch, or to preparing the next batch) while the copy runs.
+    NS_CUDA(cudaMemcpyAsync(r.d_blob, r.h_in, b->up_bytes, cudaMemcpyHostToDevice, r.stream));
+    NS_CUDA(cudaEventRecord(r.ev_h2d, r.stream));
     *out = b.release();
     return NS_OK;
+}
+
+extern "C" int ns_batch_prepare(ns_index* idx, uint32_t Q, int k_in, const uint64_t* q_off, const ns_qterm* terms,
+                                ns_batch** out) {
+    if (!idx) { set_error("ns_batch_prepare: null argument"); return NS_ERR_INVALID; }
+    return nsb::batch_prepare_on(idx, nsb::index_live_state(idx), Q, k_in, q_off, terms, out);
 }
 
 extern "C" int ns_batch_set_splits(ns_batch* b, uint32_t splits) {
     if (!b) return NS_ERR_INVALID;
     NS_CUDA(cudaSetDevice(b->st->device));
     if (b->launched) NS_CUDA(cudaEventSynchronize(b->res->ev[2]));
-    build_items(b, std::min<uint32_t>(splits, kMaxSplit));
+    const size_t items_bytes = build_items(b, std::min<uint32_t>(splits, kMaxSplit));
     BatchRes& r = *b->res;
-    NS_CUDA(cudaMemcpyAsync(r.d_blob + b->off_items, r.h_in + b->off_items, b->in_bytes - b->off_items,
-                            cudaMemcpyHostToDevice, r.stream));
-    NS_CUDA(cudaStreamSynchronize(r.stream));
+    NS_CUDA(cudaMemcpyAsync(r.d_blob + b->off_items, r.h_in + b->off_items, items_bytes, cudaMemcpyHostToDevice, r.stream));
+    NS_CUDA(cudaEventRecord(r.ev_h2d, r.stream));
     return NS_OK;
 }
 
-extern "C" int ns_batch_launch(ns_batch* b, void* stream) {
-    if (!b) { set_error("ns_batch_launch: null"); return NS_ERR_INVALID; }
-    NS_CUDA(cudaSetDevice(b->st->device));
-    cudaStream_t s = stream ? (cudaStream_t)stream : b->res->stream;
+namespace {
+
+// Enqueues [zero control + results] [impact pre-pass] [score + top-k (+ publish to peers)] on stream s.
+int launch_score(ns_batch* b, cudaStream_t s, const PublishDest* d_pub, uint32_t epoch) {
+    NS_CUDA(cudaStreamWaitEvent(s, b->res->ev_h2d, 0));
     NS_CUDA(cudaEventRecord(b->res->ev[0], s));
     if (b->Q > 0) {
-        // work-queue head + per-query locks, and the shared result lists the items merge into
-        NS_CUDA(cudaMemsetAsync(b->d_counter, 0, 4 + (size_t)b->Q * 4, s));
-        NS_CUDA(cudaMemsetAsync(b->d_out, 0, b->out_bytes, s));
+        NS_CUDA(cudaMemsetAsync(b->res->d_blob + b->off_zero, 0, b->zero_bytes, s));
         ScoreArgs a;
         a.segs = b->st->d_segs;
         a.tile_base = b->st->d_tile_base;
@@ -776,7 +1011,7 @@ extern "C" int ns_batch_launch(ns_batch* b, void* stream) {
         a.nq = b->Q;
         a.nsplit = b->nsplit_all;
         a.counter = b->d_counter;
-        a.qlock = b->d_counter + 1;
+        a.qlock = b->d_qlock;
         a.nitems = b->nitems;
         a.k = b->k;
         a.scan_always = b->scan_always ? 1u : 0u;
@@ -784,32 +1019,27 @@ extern "C" int ns_batch_launch(ns_batch* b, void* stream) {
         a.zero = 0u;
         a.impacts = reinterpret_cast<const uint2*>(b->res->d_scratch);
         a.any_scratch = (b->impact && b->ndist > 0) ? 1u : 0u;
-        {
-            // next-window L2 prefetch pays when the items of a window really run together: window-major
-            // order and enough queries to fill the machine (NSB200_L2_PREFETCH=0/1 overrides)
-            static const char* env = std::getenv("NSB200_L2_PREFETCH");
-            a.l2_prefetch = env ? (std::atoi(env) != 0 ? 1u : 0u) : (b->window_major && b->Q >= 256 ? 1u : 0u);
-        }
+        // next-window L2 prefetch pays when the items of a window really run together: window-major
+        // order and enough queries to fill the machine (NSB200_L2_PREFETCH=0/1 overrides)
+        const int pf = b->owner->tun.l2_prefetch;
+        a.l2_prefetch = pf >= 0 ? (uint32_t)pf : (b->window_major && b->Q >= 256 ? 1u : 0u);
         a.hits = b->d_out_hits;
         a.nhits = b->d_out_n;
         a.found = b->d_out_found;
-        static const bool no_fast = std::getenv("NSB200_NO_FAST") != nullptr;
-        const bool fast = b->fast && !no_fast;
+        a.pub = d_pub;
+        a.pub_epoch = epoch;
+        a.pub_pad = 0;
+        a.pub_off_n = b->off_n;
+        a.pub_off_found = b->off_found;
+        a.q_done = b->d_qdone;
+        a.n_published = b->d_npub;
+        const bool fast = b->fast && !b->owner->tun.no_fast;
         const KernelCfg cfg = pick_kernel(b->k, fast, b->impact, b->max_in_seg > 32u);
         const uint32_t warps_per_block = (uint32_t)cfg.threads / 32u;
-        // the smem opt-in and the occupancy query cost ~0.4 ms of host time per call: once per
-        // (device, kernel variant)
         int per_sm = 0;
         {
-            std::lock_guard<std::mutex> lk(b->owner->mu);
-            auto it = b->owner->occupancy.find(cfg.fn);
-            if (it == b->owner->occupancy.end()) {
-                NS_CUDA(cudaFuncSetAttribute(cfg.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
-                NS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cfg.fn, cfg.threads, cfg.smem));
-                b->owner->occupancy[cfg.fn] = per_sm;
-            } else {
-                per_sm = it->second;
-            }
+            auto it = b->owner->occupancy.find(cfg.fn);  // filled at ns_index_create, read-only afterwards
+            if (it != b->owner->occupancy.end()) per_sm = it->second;
         }
         if (per_sm < 1) { set_error("score kernel does not fit on an SM"); return NS_ERR_CUDA; }
         uint32_t grid = (uint32_t)b->owner->sm_count * (uint32_t)per_sm;
@@ -832,10 +1062,19 @@ extern "C" int ns_batch_launch(ns_batch* b, void* stream) {
         }
         void* kargs[] = {(void*)&a};
         NS_CUDA(cudaLaunchKernel(cfg.fn, dim3(grid), dim3(cfg.threads), kargs, cfg.smem, s));
-        NS_CUDA(cudaEventRecord(b->res->ev[1], s));
-    } else {
-        NS_CUDA(cudaEventRecord(b->res->ev[1], s));
     }
+    NS_CUDA(cudaEventRecord(b->res->ev[1], s));
+    return NS_OK;
+}
+
+}  // namespace
+
+extern "C" int ns_batch_launch(ns_batch* b, void* stream) {
+    if (!b) { set_error("ns_batch_launch: null"); return NS_ERR_INVALID; }
+    NS_CUDA(cudaSetDevice(b->st->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : b->res->stream;
+    int rc = launch_score(b, s, nullptr, 0u);
+    if (rc != NS_OK) return rc;
     NS_CUDA(cudaEventRecord(b->res->ev[2], s));
     b->launched = true;
     return NS_OK;
@@ -866,9 +1105,10 @@ extern "C" void ns_batch_destroy(ns_batch* b) {
     if (!b) return;
     cudaSetDevice(b->st->device);
     if (b->launched) cudaEventSynchronize(b->res->ev[2]);
+    else if (b->res) cudaEventSynchronize(b->res->ev_h2d);  // the pinned blob goes back to the pool: the copy must be done
     if (b->owner && b->res) {
         std::lock_guard<std::mutex> lk(b->owner->mu);
-        if (b->owner->pool.size() < 64) b->owner->pool.push_back(std::move(b->res));
+        if (!b->owner->closed && b->owner->pool.size() < 64) b->owner->pool.push_back(std::move(b->res));
     }
     delete b;
 }
@@ -882,10 +1122,13 @@ extern "C" int ns_batch_device_results(ns_batch* b, void** d_hits, void** d_nhit
 }
 
 extern "C" uint64_t ns_batch_posting_count(const ns_batch* b) { return b ? b->postings : 0; }
+extern "C" void* ns_batch_stream(ns_batch* b) { return b && b->res ? (void*)b->res->stream : nullptr; }
 extern "C" uint32_t ns_batch_num_launches(const ns_batch* b) {
     if (!b || b->Q == 0) return 0u;
     return 1u + (b->impact && b->ndist > 0 ? 1u : 0u);
 }
+extern "C" uint64_t ns_batch_upload_bytes(const ns_batch* b) { return b ? b->up_bytes : 0; }
+extern "C" uint64_t ns_batch_result_bytes(const ns_batch* b) { return b ? b->out_bytes : 0; }
 
 extern "C" float ns_batch_last_kernel_ms(ns_batch* b, int which) {
     if (!b || !b->launched || which < 0 || which > 1) return -1.0f;
@@ -898,7 +1141,7 @@ extern "C" float ns_batch_last_kernel_ms(ns_batch* b, int which) {
 
 extern "C" int ns_search_batch(ns_index* idx, uint32_t Q, int k, const uint64_t* q_off, const ns_qterm* terms,
                                ns_hit* out_hits, uint32_t* out_nhits, uint64_t* out_found) {
-    static const bool trace = std::getenv("NSB200_TRACE") != nullptr;
+    if (!idx) { set_error("ns_search_batch: null index"); return NS_ERR_INVALID; }
     auto now = [] { return std::chrono::steady_clock::now(); };
     auto t0 = now();
     ns_batch* b = nullptr;
@@ -912,7 +1155,7 @@ extern "C" int ns_search_batch(ns_index* idx, uint32_t Q, int k, const uint64_t*
     const uint32_t nitems = b->nitems;
     ns_batch_destroy(b);
     auto t4 = now();
-    if (trace) {
+    if (idx->sh->tun.trace) {
         auto ms = [](auto a, auto c) { return std::chrono::duration<double, std::milli>(c - a).count(); };
         std::fprintf(stderr, "[nsb200] Q=%u items=%u prepare %.3f ms, launch %.3f, fetch(+kernels) %.3f, destroy %.3f\n", Q,
                      nitems, ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, t4));
@@ -977,6 +1220,222 @@ extern "C" int ns_merge_blobs_device(int device, uint32_t Q, int k, uint32_t nli
     const unsigned char* base = static_cast<const unsigned char*>(d_blobs);
     return merge_launch(device, Q, k, nlists, base, base + off_nhits, base + off_found, blob_stride, blob_stride,
                         blob_stride, d_out_hits, d_out_nhits, d_out_found, stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Peer exchange (multi-GPU): result blobs travel as P2P stores issued by the score kernel itself.
+// ---------------------------------------------------------------------------------------------
+
+namespace {
+
+size_t blob_capacity(uint32_t max_q) {
+    return align_up(std::max<size_t>(1, (size_t)max_q * NS_MAX_K) * sizeof(ns_hit)) + align_up(std::max<size_t>(1, max_q) * 4) +
+           align_up(std::max<size_t>(1, max_q) * 8);
+}
+
+int upload_pub(ns_exchange* x) {
+    std::vector<PublishDest> h(x->slots);
+    for (uint32_t s = 0; s < x->slots; s++) {
+        PublishDest& p = h[s];
+        std::memset(&p, 0, sizeof(p));
+        p.ndest = (uint32_t)x->dests.size();
+        p.src = x->rank;
+        p.stride = x->stride;
+        for (size_t d = 0; d < x->dests.size(); d++) {
+            p.blob[d] = x->gather(x->dests[d].base, s);
+            p.flag[d] = x->flags(x->dests[d].base, s);
+        }
+    }
+    NS_CUDA(cudaSetDevice(x->device));
+    NS_CUDA(cudaMemcpy(x->pub(0), h.data(), h.size() * sizeof(PublishDest), cudaMemcpyHostToDevice));
+    return NS_OK;
+}
+
+}  // namespace
+
+extern "C" int ns_exchange_create(int device, uint32_t world, uint32_t rank, uint32_t max_queries, uint32_t slots,
+                                  ns_exchange** out) {
+    if (!out || world == 0 || world > NS_MAX_PEERS || rank >= world || slots == 0 || slots > 8 || max_queries == 0) {
+        set_error("ns_exchange_create: bad argument (world <= NS_MAX_PEERS, rank < world, 1 <= slots <= 8)");
+        return NS_ERR_INVALID;
+    }
+    *out = nullptr;
+    NS_CUDA(cudaSetDevice(device));
+    auto x = std::make_unique<ns_exchange>();
+    x->device = device;
+    x->world = world;
+    x->rank = rank;
+    x->slots = slots;
+    x->max_q = max_queries;
+    x->stride = blob_capacity(max_queries);
+    x->slot_bytes = (size_t)world * x->stride;
+    x->off_flags = (size_t)slots * x->slot_bytes;
+    x->off_status = x->off_flags + (size_t)slots * 256;
+    x->off_merged = x->off_status + (size_t)slots * 256;
+    x->off_pub = x->off_merged + (size_t)slots * x->stride;
+    x->total = x->off_pub + align_up((size_t)slots * sizeof(PublishDest));
+    if (const char* s = std::getenv("NSB200_EXCHANGE_TIMEOUT_MS")) x->timeout_ns = (uint64_t)std::max(1L, std::atol(s)) * 1000000ull;
+    cudaError_t e = cudaMalloc(&x->d_mem, x->total);
+    // flags and status start at 0; epochs start at 1
+    if (e == cudaSuccess) e = cudaMemset(x->d_mem + x->off_flags, 0, x->off_merged - x->off_flags);
+    if (e == cudaSuccess) e = cudaMallocHost(&x->h_out, x->stride + 256);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&x->stream, cudaStreamNonBlocking);
+    for (uint32_t s = 0; e == cudaSuccess && s < slots; s++) e = cudaEventCreateWithFlags(&x->ev_done[s], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        set_error(std::string("ns_exchange_create: ") + cudaGetErrorString(e));
+        ns_exchange_destroy(x.release());
+        return NS_ERR_CUDA;
+    }
+    *out = x.release();
+    return NS_OK;
+}
+
+extern "C" void ns_exchange_destroy(ns_exchange* x) {
+    if (!x) return;
+    cudaSetDevice(x->device);
+    cudaDeviceSynchronize();
+    for (auto& d : x->dests)
+        if (d.ipc && d.base) cudaIpcCloseMemHandle(d.base);
+    if (x->d_mem) cudaFree(x->d_mem);
+    if (x->h_out) cudaFreeHost(x->h_out);
+    for (auto& ev : x->ev_done)
+        if (ev) cudaEventDestroy(ev);
+    if (x->stream) cudaStreamDestroy(x->stream);
+    delete x;
+}
+
+extern "C" int ns_exchange_ipc_handle(ns_exchange* x, void* handle) {
+    if (!x || !handle) { set_error("ns_exchange_ipc_handle: null"); return NS_ERR_INVALID; }
+    static_assert(sizeof(cudaIpcMemHandle_t) == NS_IPC_HANDLE_BYTES, "handle size");
+    NS_CUDA(cudaSetDevice(x->device));
+    cudaIpcMemHandle_t h;
+    NS_CUDA(cudaIpcGetMemHandle(&h, x->d_mem));
+    std::memcpy(handle, &h, sizeof(h));
+    return NS_OK;
+}
+
+static int add_dest(ns_exchange* x, uint32_t peer_rank, uint8_t* base, bool ipc) {
+    std::lock_guard<std::mutex> lk(x->mu);
+    if (x->dests.size() >= (size_t)kMaxPeers) { set_error("ns_exchange: too many destinations"); return NS_ERR_INVALID; }
+    for (auto& d : x->dests)
+        if (d.rank == peer_rank) { set_error("ns_exchange: destination attached twice"); return NS_ERR_INVALID; }
+    x->dests.push_back(ns_exchange::Dest{peer_rank, base, ipc});
+    if (peer_rank == x->rank) x->receiver = true;
+    return upload_pub(x);
+}
+
+extern "C" int ns_exchange_attach_ipc(ns_exchange* x, uint32_t peer_rank, const void* handle) {
+    if (!x || !handle || peer_rank >= x->world || peer_rank == x->rank) { set_error("ns_exchange_attach_ipc: bad argument"); return NS_ERR_INVALID; }
+    NS_CUDA(cudaSetDevice(x->device));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof(h));
+    void* p = nullptr;
+    NS_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    return add_dest(x, peer_rank, static_cast<uint8_t*>(p), true);
+}
+
+extern "C" int ns_exchange_attach_local(ns_exchange* x, ns_exchange* peer) {
+    if (!x || !peer) { set_error("ns_exchange_attach_local: null"); return NS_ERR_INVALID; }
+    if (peer->world != x->world || peer->stride != x->stride || peer->slots != x->slots) {
+        set_error("ns_exchange_attach_local: the two exchanges were created with different shapes");
+        return NS_ERR_INVALID;
+    }
+    NS_CUDA(cudaSetDevice(x->device));
+    if (peer->device != x->device) {
+        int can = 0;
+        NS_CUDA(cudaDeviceCanAccessPeer(&can, x->device, peer->device));
+        if (!can) { set_error("ns_exchange_attach_local: no peer access between the two devices"); return NS_ERR_CUDA; }
+        cudaError_t e = cudaDeviceEnablePeerAccess(peer->device, 0);
+        if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+        else if (e != cudaSuccess) { set_error(std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e)); return NS_ERR_CUDA; }
+    }
+    return add_dest(x, peer->rank, peer->d_mem, false);
+}
+
+extern "C" int ns_batch_launch_exchange(ns_batch* b, ns_exchange* x, uint64_t step, void* stream) {
+    if (!b || !x) { set_error("ns_batch_launch_exchange: null"); return NS_ERR_INVALID; }
+    if (b->st->device != x->device) { set_error("ns_batch_launch_exchange: batch and exchange live on different devices"); return NS_ERR_INVALID; }
+    if (b->out_bytes > x->stride) { set_error("ns_batch_launch_exchange: batch larger than the exchange was created for"); return NS_ERR_INVALID; }
+    if (x->dests.empty()) { set_error("ns_batch_launch_exchange: no destination attached"); return NS_ERR_STATE; }
+    NS_CUDA(cudaSetDevice(x->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : b->res->stream;
+    const uint32_t slot = (uint32_t)(step % x->slots);
+    const uint32_t epoch = (uint32_t)(step / x->slots) + 1u;
+    // Q == 0: nothing to score, nothing to publish (the merge of an empty batch is a no-op as well)
+    int rc = launch_score(b, s, b->Q ? x->pub(slot) : nullptr, epoch);
+    if (rc != NS_OK) return rc;
+    NS_CUDA(cudaEventRecord(b->res->ev[2], s));
+    b->launched = true;
+    return NS_OK;
+}
+
+extern "C" int ns_exchange_merge(ns_exchange* x, uint64_t step, uint32_t Q, int k_in, int spin, void* stream) {
+    if (!x) { set_error("ns_exchange_merge: null"); return NS_ERR_INVALID; }
+    if (!x->receiver) { set_error("ns_exchange_merge: this rank does not receive (it is not among its own destinations)"); return NS_ERR_STATE; }
+    const uint32_t k = (uint32_t)std::max(1, std::min(k_in, NS_MAX_K));
+    const size_t off_n = align_up(std::max<size_t>(1, (size_t)Q * k) * sizeof(ns_hit));
+    const size_t off_found = off_n + align_up(std::max<size_t>(1, Q) * 4);
+    if (off_found + align_up(std::max<size_t>(1, Q) * 8) > x->stride) { set_error("ns_exchange_merge: Q, k larger than the exchange was created for"); return NS_ERR_INVALID; }
+    NS_CUDA(cudaSetDevice(x->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : x->stream;
+    const uint32_t slot = (uint32_t)(step % x->slots);
+    const uint32_t epoch = (uint32_t)(step / x->slots) + 1u;
+    if (Q) {
+        if (spin) {
+            exchange_wait_kernel<<<1, 32, 0, s>>>(x->flags(x->d_mem, slot), x->world, epoch, x->timeout_ns, x->status(slot));
+            NS_CUDA(cudaGetLastError());
+        }
+        uint8_t* g = x->gather(x->d_mem, slot);
+        uint8_t* m = x->merged(slot);
+        int rc = merge_launch(x->device, Q, (int)k, x->world, g, g + off_n, g + off_found, x->stride, x->stride, x->stride, m,
+                              m + off_n, m + off_found, s);
+        if (rc != NS_OK) return rc;
+    }
+    NS_CUDA(cudaEventRecord(x->ev_done[slot], s));
+    return NS_OK;
+}
+
+extern "C" int ns_exchange_result_device(ns_exchange* x, uint64_t step, void** d_blob) {
+    if (!x || !d_blob) return NS_ERR_INVALID;
+    *d_blob = x->merged((uint32_t)(step % x->slots));
+    return NS_OK;
+}
+
+extern "C" int ns_exchange_fetch(ns_exchange* x, uint64_t step, uint32_t Q, int k_in, ns_hit* out_hits,
+                                 uint32_t* out_nhits, uint64_t* out_found) {
+    if (!x) { set_error("ns_exchange_fetch: null"); return NS_ERR_INVALID; }
+    if (!x->receiver) { set_error("ns_exchange_fetch: this rank does not receive (it is not among its own destinations)"); return NS_ERR_STATE; }
+    const uint32_t k = (uint32_t)std::max(1, std::min(k_in, NS_MAX_K));
+    const size_t sz_hits = align_up(std::max<size_t>(1, (size_t)Q * k) * sizeof(ns_hit));
+    const size_t sz_n = align_up(std::max<size_t>(1, Q) * 4);
+    const size_t sz_found = align_up(std::max<size_t>(1, Q) * 8);
+    const size_t bytes = sz_hits + sz_n + sz_found;
+    if (bytes > x->stride) { set_error("ns_exchange_fetch: Q, k larger than the exchange was created for"); return NS_ERR_INVALID; }
+    NS_CUDA(cudaSetDevice(x->device));
+    const uint32_t slot = (uint32_t)(step % x->slots);
+    std::lock_guard<std::mutex> lk(x->mu);
+    NS_CUDA(cudaStreamWaitEvent(x->stream, x->ev_done[slot], 0));
+    if (Q) NS_CUDA(cudaMemcpyAsync(x->h_out, x->merged(slot), bytes, cudaMemcpyDeviceToHost, x->stream));
+    NS_CUDA(cudaMemcpyAsync(x->h_out + x->stride, x->status(slot), 4, cudaMemcpyDeviceToHost, x->stream));
+    NS_CUDA(cudaStreamSynchronize(x->stream));
+    uint32_t st = 0;
+    std::memcpy(&st, x->h_out + x->stride, 4);
+    if (st != 0) {
+        cudaMemsetAsync(x->status(slot), 0, 4, x->stream);
+        cudaStreamSynchronize(x->stream);
+        char buf[160];
+        std::snprintf(buf, sizeof(buf), "ns_exchange_fetch: step %llu timed out waiting for the result blobs of ranks (bit mask) 0x%x",
+                      (unsigned long long)step, st);
+        set_error(buf);
+        return NS_ERR_STATE;
+    }
+    if (Q) {
+        if (out_hits) std::memcpy(out_hits, x->h_out, (size_t)Q * k * sizeof(ns_hit));
+        if (out_nhits) std::memcpy(out_nhits, x->h_out + sz_hits, (size_t)Q * 4);
+        if (out_found) std::memcpy(out_found, x->h_out + sz_hits + sz_n, (size_t)Q * 8);
+    }
+    return NS_OK;
 }
 
 extern "C" int ns_selftest_fastdiv(int device, uint64_t n, uint64_t seed, uint64_t* mismatches) {

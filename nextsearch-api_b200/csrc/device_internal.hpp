@@ -1,0 +1,21 @@
+// Internal C++ seam between the host engine (host/engine.cpp) and the device layer (device_api.cu);
+// not part of the C ABI.  The engine binds every call to ONE committed index generation: it snapshots
+// the device state together with its host lexicons and prepares batches against exactly that state,
+// so a concurrent ns_engine_reload can never pair old lexicon rows with a new device index.
+#pragma once
+#include <cstdint>
+#include <memory>
+
+#include "../../include/nextsearch_b200.h"
+
+namespace nsb {
+
+// The committed device index of `idx` right now (nullptr before the first commit).  Holding the pointer
+// keeps that generation's device memory alive.
+std::shared_ptr<const void> index_live_state(ns_index* idx);
+
+// ns_batch_prepare against an explicit generation.
+int batch_prepare_on(ns_index* idx, const std::shared_ptr<const void>& state, uint32_t Q, int k, const uint64_t* q_off,
+                     const ns_qterm* terms, ns_batch** out);
+
+}  // namespace nsb

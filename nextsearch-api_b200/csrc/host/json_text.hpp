@@ -199,9 +199,7 @@ inline bool valid_utf8(const char* s, size_t n) {
         else if (c >= 0xF1 && c <= 0xF3) need = 3;
         else if (c == 0xF4) { need = 3; hi = 0x8F; }
         else return false;
-        if (i + need >= n + 0 && i + need > n - 1 + 0) {
-            if (i + need > n - 1) return false;
-        }
+        if (i + need >= n) return false;  // truncated sequence
         if (p[i + 1] < lo || p[i + 1] > hi) return false;
         for (size_t j = 2; j <= need; j++)
             if (p[i + j] < 0x80 || p[i + j] > 0xBF) return false;

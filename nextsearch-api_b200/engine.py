@@ -85,6 +85,11 @@ class Batch:
         return int(self._lib.ns_batch_posting_count(self._h))
 
     @property
+    def stream(self) -> int:
+        """The batch's own CUDA stream (launch(None) uses it)."""
+        return int(self._lib.ns_batch_stream(self._h) or 0)
+
+    @property
     def num_launches(self) -> int:
         return int(self._lib.ns_batch_num_launches(self._h))
 
@@ -163,6 +168,62 @@ class DeviceIndex:
         if self._h and self._own:
             self._lib.ns_index_destroy(self._h)
         self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Exchange:
+    """ns_exchange: peer exchange of per-GPU result blobs, published by the score kernel itself (P2P stores).
+
+    One per rank.  ``attach(peer)`` adds an exchange of this process as a destination (``attach(self)`` makes this
+    rank a receiver: it waits for all ``world`` blobs of a step and merges them); ``attach_ipc`` adds a rank
+    living in another process through its 64-byte handle."""
+
+    def __init__(self, device: int, world: int, rank: int, max_queries: int, slots: int = 2):
+        self._lib = _lib.load()
+        h = C.c_void_p()
+        check(self._lib.ns_exchange_create(int(device), int(world), int(rank), int(max_queries), int(slots), C.byref(h)))
+        self._h = h
+        self.device, self.world, self.rank, self.slots = device, world, rank, slots
+        self._peers = []  # keep attached local peers alive
+
+    def ipc_handle(self) -> bytes:
+        buf = C.create_string_buffer(_lib.NS_IPC_HANDLE_BYTES)
+        check(self._lib.ns_exchange_ipc_handle(self._h, buf))
+        return buf.raw
+
+    def attach(self, peer: "Exchange") -> None:
+        check(self._lib.ns_exchange_attach_local(self._h, peer._h))
+        if peer is not self:
+            self._peers.append(peer)
+
+    def attach_ipc(self, peer_rank: int, handle: bytes) -> None:
+        check(self._lib.ns_exchange_attach_ipc(self._h, int(peer_rank), C.c_char_p(handle)))
+
+    def launch(self, batch: "Batch", step: int, stream: Optional[int] = None) -> None:
+        check(self._lib.ns_batch_launch_exchange(batch._h, self._h, int(step), C.c_void_p(stream) if stream else None))
+
+    def merge(self, step: int, Q: int, k: int, spin: bool = True, stream: Optional[int] = None) -> None:
+        check(self._lib.ns_exchange_merge(self._h, int(step), int(Q), int(k), 1 if spin else 0,
+                                          C.c_void_p(stream) if stream else None))
+
+    def fetch(self, step: int, Q: int, k: int) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        K = clamp_k(k)
+        hits = np.zeros((Q, K), dtype=HIT_DTYPE)
+        nhits = np.zeros(Q, dtype=np.uint32)
+        found = np.zeros(Q, dtype=np.uint64)
+        check(self._lib.ns_exchange_fetch(self._h, int(step), int(Q), int(k), _ptr(hits), _ptr(nhits), _ptr(found)))
+        return hits, nhits, found
+
+    def close(self) -> None:
+        if self._h:
+            self._lib.ns_exchange_destroy(self._h)
+            self._h = None
+        self._peers = []
 
     def __del__(self):
         try:
