@@ -234,6 +234,12 @@ typedef struct ns_engine ns_engine;
 
 /* device < 0: host-only engine (lexicon / tokeniser / resolve available, search fails loudly) */
 int ns_engine_create(const char* index_dir, int device, ns_engine** out);
+/* One engine spanning `ndev` GPUs of the box (ns_index_create(ndev, dev_ids)): segment j of the
+ * engine's share lives on devices[j % ndev]; a batch is tokenised and resolved once, scored on every device,
+ * the per-device results are stored into devices[0]'s gather buffer by the score kernels (peer memory) and
+ * merged there.  This is what a C++ api_server links: one process, one handle, all GPUs.  ndev = 0: host-only. */
+int ns_engine_create_multi(const char* index_dir, int ndev, const int* devices, ns_engine** out);
+int ns_engine_num_devices(const ns_engine* e);
 void ns_engine_destroy(ns_engine* e);
 
 /* Shard selection for multi-GPU: this engine uploads only segments with
@@ -251,9 +257,11 @@ int ns_engine_segment_stats(const ns_engine* e, int i, uint32_t* N, float* avgdl
 /* df / count of `term` in segment i; returns 0 and sets *df=*count=0 if absent */
 int ns_engine_term_stats(const ns_engine* e, int i, const char* term, uint32_t* df, uint32_t* count);
 
-/* Engine::search (src/api_engine.cpp:369-542) minus the LRU cache and the
- * metadata.csv decoration: returns the reference's JSON object as text
- * (keys: query, k, segments, results[{score, segment, docId, cord_uid}], found).
+/* Engine::search (src/api_engine.cpp:369-542) minus the LRU cache: returns the reference's JSON object as
+ * text, byte-identical to nlohmann's dump() of it (keys: query, k, segments, found,
+ * results[{score, segment, docId, cord_uid} + title, url, publish_time, author when INDEX_DIR/metadata.csv
+ * has a row for the cord_uid, src/api_engine.cpp:516-532]).  NS_ERR_INVALID when the query or a result field
+ * is not valid UTF-8 (dump() throws there).
  * Writes at most cap-1 bytes + NUL; returns the full length needed (like snprintf)
  * in *needed. */
 int ns_engine_search_json(ns_engine* e, const char* query, int k, char* buf, size_t cap, size_t* needed);
@@ -280,7 +288,34 @@ int ns_engine_resolve_batch(ns_engine* e, uint32_t Q, const char* const* queries
 int ns_engine_resolve_batch_packed(ns_engine* e, uint32_t Q, const char* zqueries, size_t nbytes,
                                    uint64_t* q_off, ns_qterm* terms, uint64_t terms_cap, uint64_t* n_terms,
                                    uint8_t* has_terms);
-ns_index* ns_engine_index(ns_engine* e);
+ns_index* ns_engine_index(ns_engine* e);                    /* device slot 0 */
+ns_index* ns_engine_device_index(ns_engine* e, int slot);
+/* timing and size of the last successful reload: total seconds, seconds in barrel reads + upload (overlapped),
+ * seconds building the term dictionary, posting bytes on disk (8 B x sum of LexEntry.count), device bytes */
+int ns_engine_reload_stats(const ns_engine* e, double* total_s, double* read_upload_s, double* dict_s,
+                           uint64_t* posting_bytes, uint64_t* device_bytes);
+
+/* Explicit (term, qweight) lists — the reference's qterms_w (src/api_engine.cpp:410-421) — one per query:
+ * t_off[Q+1] indexes terms[] / weights[].  No tokenisation, filter or expansion: what the scoring loop
+ * (:426-505) receives.  A query with an empty list has no "found" (:424). */
+int ns_engine_search_terms_batch(ns_engine* e, uint32_t Q, const uint64_t* t_off, const char* const* terms,
+                                 const float* weights, int k, ns_hit* out_hits, uint32_t* out_nhits,
+                                 uint64_t* out_found, uint8_t* has_found);
+/* SemanticIndex::expand for one query (src/semantic_embedding.cpp:148-229 with the constants of
+ * src/api_engine.cpp:412-417): terms NUL-separated into buf, weights into weights[wcap]; returns the count
+ * (0 with *enabled = 0 when no embeddings file was found at reload), -1 if a buffer is too small. */
+int ns_engine_expand(ns_engine* e, const char* query, char* buf, size_t cap, float* weights, int wcap, int* enabled);
+
+/* One query, blocking — the shape of the reference's engine.search(q, k) call per HTTP request
+ * (src/api_server.cpp:117-178).  out_hits has room for clamp(k) entries.  With the coalescer running,
+ * concurrent callers are gathered into one GPU batch: a dispatcher takes up to max_batch queued requests,
+ * or whatever has arrived max_wait_us after the oldest one, and scores them together (the reference
+ * serialises them on Engine::mtx, src/api_engine.cpp:372).  ns_engine_search_json uses the same path. */
+int ns_engine_search_one(ns_engine* e, const char* query, int k, ns_hit* out_hits, uint32_t* out_nhits,
+                         uint64_t* out_found, uint8_t* has_found);
+int ns_engine_coalescer_start(ns_engine* e, uint32_t max_batch, uint32_t max_wait_us, int dispatchers);
+int ns_engine_coalescer_stop(ns_engine* e);
+int ns_engine_coalescer_stats(ns_engine* e, uint64_t* batches, uint64_t* queries, uint64_t* max_batch_seen);
 /* cord_uid of (segment, doc); returns length or -1 */
 int ns_engine_cord_uid(const ns_engine* e, uint32_t seg, uint32_t doc, char* buf, size_t cap);
 

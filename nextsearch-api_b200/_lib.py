@@ -92,6 +92,16 @@ SYMBOLS = {
                                         _P, _P, _P, _P]),
     "ns_selftest_fastdiv": (C.c_int, [C.c_int, C.c_uint64, C.c_uint64, _u64p]),
     "ns_engine_create": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(_P)]),
+    "ns_engine_create_multi": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(_P)]),
+    "ns_engine_num_devices": (C.c_int, [_P]),
+    "ns_engine_device_index": (_P, [_P, C.c_int]),
+    "ns_engine_reload_stats": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), _u64p, _u64p]),
+    "ns_engine_search_terms_batch": (C.c_int, [_P, C.c_uint32, _P, _strs, _P, C.c_int, _P, _P, _P, _P]),
+    "ns_engine_expand": (C.c_int, [_P, C.c_char_p, C.c_char_p, C.c_size_t, _P, C.c_int, C.POINTER(C.c_int)]),
+    "ns_engine_search_one": (C.c_int, [_P, C.c_char_p, C.c_int, _P, _u32p, _u64p, _u8p]),
+    "ns_engine_coalescer_start": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_int]),
+    "ns_engine_coalescer_stop": (C.c_int, [_P]),
+    "ns_engine_coalescer_stats": (C.c_int, [_P, _u64p, _u64p, _u64p]),
     "ns_engine_destroy": (None, [_P]),
     "ns_engine_set_shard": (C.c_int, [_P, C.c_int, C.c_int]),
     "ns_engine_reload": (C.c_int, [_P]),

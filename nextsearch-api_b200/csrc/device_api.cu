@@ -1396,6 +1396,17 @@ extern "C" int ns_exchange_merge(ns_exchange* x, uint64_t step, uint32_t Q, int 
     return NS_OK;
 }
 
+int nsb::exchange_root_merge(ns_exchange* root, ns_batch* const* batches, int ndev, uint64_t step, uint32_t Q, int k) {
+    if (!root || !batches || ndev < 1 || !batches[0]) { set_error("exchange_root_merge: null"); return NS_ERR_INVALID; }
+    NS_CUDA(cudaSetDevice(root->device));
+    cudaStream_t s = batches[0]->res->stream;
+    for (int d = 1; d < ndev; d++) {
+        if (!batches[d] || !batches[d]->launched) { set_error("exchange_root_merge: a device's batch was not launched"); return NS_ERR_STATE; }
+        NS_CUDA(cudaStreamWaitEvent(s, batches[d]->res->ev[2], 0));  // recorded right after that device's score kernel
+    }
+    return ns_exchange_merge(root, step, Q, k, 0, s);
+}
+
 extern "C" int ns_exchange_result_device(ns_exchange* x, uint64_t step, void** d_blob) {
     if (!x || !d_blob) return NS_ERR_INVALID;
     *d_blob = x->merged((uint32_t)(step % x->slots));

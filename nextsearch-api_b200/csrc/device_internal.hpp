@@ -18,4 +18,9 @@ std::shared_ptr<const void> index_live_state(ns_index* idx);
 int batch_prepare_on(ns_index* idx, const std::shared_ptr<const void>& state, uint32_t Q, int k, const uint64_t* q_off,
                      const ns_qterm* terms, ns_batch** out);
 
+// Multi-device engine, root side of one step: order the root batch's stream after the score kernels of every
+// other device's batch (events — same process, so nothing has to poll) and enqueue the merge of the `ndev`
+// blobs the score kernels stored into the root's gather buffer.  batches[0] is the root's.
+int exchange_root_merge(ns_exchange* root, ns_batch* const* batches, int ndev, uint64_t step, uint32_t Q, int k);
+
 }  // namespace nsb

@@ -1,43 +1,43 @@
 // Host mirror of cord19::Engine for the search path (reference: include/api_engine.hpp:23-91,
-// src/api_engine.cpp:50-90 and :369-542), plus the corpus tooling entry points.
+// src/api_engine.cpp:50-162 and :369-542), plus the corpus tooling entry points.
 // Tokenise / stop-filter / lexicon lookup / IDF stay on the host exactly as in the reference;
-// the per-posting work goes through ns_search_batch.
+// the per-posting work goes to the GPU(s) through the device layer (device_api.cu).
+//
+// Differences in shape, all deliberate:
+//   * one engine may span several GPUs of the box (segment j of the engine's share lives on device
+//     j % ndev); a batch is tokenised and resolved ONCE, fanned out, scored on every device, the per-device
+//     result blobs are stored into device 0's gather buffer by the score kernels themselves (peer memory)
+//     and merged there — the reference's loop over segments (src/api_engine.cpp:441-505) spread out;
+//   * everything a search needs — segment names, lexicons, cord_uids, metadata, embeddings and the
+//     device arrays — forms one immutable GENERATION that a call snapshots once; reload builds a new one
+//     and swaps it in (the reference holds Engine::mtx for the whole search, :372);
+//   * single queries may be coalesced into batches by a dispatcher (ns_engine_coalescer_start).
 #include <algorithm>
-#include <cstdlib>
 #include <atomic>
-#include <charconv>
 #include <chrono>
+#include <condition_variable>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <memory>
 #include <mutex>
-#include <shared_mutex>
 #include <string>
 #include <thread>
 #include <vector>
 
 #include "../../../include/nextsearch_b200.h"
+#include "../device_internal.hpp"
 #include "common.hpp"
 #include "corpus.hpp"
+#include "json_text.hpp"
+#include "metadata.hpp"
 #include "segment_io.hpp"
+#include "semantic.hpp"
 #include "textutil.hpp"
 #include "workpool.hpp"
 
 using namespace nsb;
-
-struct ns_engine {
-    std::string index_dir;
-    int device = -1;
-    int rank = 0, world = 1;
-    ns_index* idx = nullptr;
-    mutable std::shared_mutex mu;  // reload takes it exclusively; searches share it
-    std::vector<std::string> seg_names;
-    // segs[i] is loaded only when this engine owns segment i (i % world == rank)
-    std::vector<std::unique_ptr<HostSegment>> segs;
-    bool owns(size_t i) const { return (int)(i % (size_t)world) == rank; }
-    std::unique_ptr<WorkPool> pool;  // query front-end workers, created on first batch
-    std::once_flag pool_once;
-};
 
 namespace {
 
@@ -46,236 +46,293 @@ int hw_threads() {
     return n == 0 ? 1 : (int)n;
 }
 
-void json_escape(const std::string& s, std::string& out) {
-    for (unsigned char c : s) {
-        switch (c) {
-            case '"': out += "\\\""; break;
-            case '\\': out += "\\\\"; break;
-            case '\b': out += "\\b"; break;
-            case '\f': out += "\\f"; break;
-            case '\n': out += "\\n"; break;
-            case '\r': out += "\\r"; break;
-            case '\t': out += "\\t"; break;
-            default:
-                if (c < 0x20) {
-                    char buf[8];
-                    std::snprintf(buf, sizeof(buf), "\\u%04x", c);
-                    out += buf;
-                } else {
-                    out.push_back((char)c);
-                }
+// One committed state of the engine.  Immutable after publication.
+struct Generation {
+    std::vector<std::string> seg_names;
+    std::vector<std::unique_ptr<HostSegment>> segs;  // loaded only for segments this engine owns
+    std::vector<int> seg_dev;                         // device slot of each owned segment, -1 otherwise
+    TermDict dict;
+    std::vector<std::vector<uint32_t>> dev_cols;      // per device slot: the dict columns (owned segments) it holds, ascending
+    std::vector<std::shared_ptr<const void>> dev_state;  // per device slot: the committed device index
+    MetaIndex meta;
+    SemanticIndex sem;
+    double load_seconds = 0, upload_seconds = 0;
+    uint64_t posting_bytes = 0;
+};
+
+struct ReloadStats {
+    double total_s = 0, read_s = 0, dict_s = 0;
+    uint64_t posting_bytes = 0;
+};
+
+// Exchange group of a multi-device engine: one ns_exchange per device, every device publishes into the
+// root's (device slot 0) gather buffer; slots = 1 because a call owns its group until it has fetched.
+struct XGroup {
+    std::vector<ns_exchange*> x;
+    uint32_t max_q = 0;
+    uint64_t step = 0;
+    ~XGroup() {
+        for (auto* e : x)
+            if (e) ns_exchange_destroy(e);
+    }
+};
+
+struct Coalescer;
+
+}  // namespace
+
+struct ns_engine {
+    std::string index_dir;
+    std::vector<int> devices;       // CUDA ordinals, empty = host-only engine
+    std::vector<ns_index*> idx;     // one per device slot
+    int rank = 0, world = 1;        // process-level share: segment i is owned when i % world == rank
+    bool keep_raw = false;          // NSB200_KEEP_RAW (read at create): keep {docId, tf} next to the resident scores, so that
+                                    // batches through the raw ABI may name a row with a foreign idf
+    std::mutex gen_mu;              // guards `gen` (the pointer only)
+    std::shared_ptr<const Generation> gen;
+    std::mutex reload_mu;           // one reload at a time
+    std::unique_ptr<WorkPool> pool;
+    std::once_flag pool_once;
+    std::mutex xg_mu;
+    std::vector<std::unique_ptr<XGroup>> xg_pool;
+    std::unique_ptr<Coalescer> coalescer;
+    std::mutex co_mu;               // guards `coalescer` start/stop
+    ReloadStats last_reload;
+
+    std::shared_ptr<const Generation> snapshot() {
+        std::lock_guard<std::mutex> lk(gen_mu);
+        return gen;
+    }
+    bool owns(size_t i) const { return (int)(i % (size_t)world) == rank; }
+    WorkPool& workers() {
+        std::call_once(pool_once, [&] {
+            int n = std::min(hw_threads(), 16);
+            if (const char* s = std::getenv("NSB200_HOST_THREADS")) n = std::max(1, std::atoi(s));
+            // a sharded engine is one of `world` processes on the same box: take a 1/world share of the cores
+            n = std::max(1, std::min(n, std::max(1, hw_threads() / std::max(1, world))));
+            pool.reset(new WorkPool(std::max(0, n - 1)));
+        });
+        return *pool;
+    }
+};
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// reload
+// ------------------------------------------------------------------------------------------
+
+// Pinned staging of one segment's postings: every barrel file that has been read starts its H2D copy.
+struct UploadSink : PostingSink {
+    ns_index* idx;
+    ns_upload* up = nullptr;
+    int rc = NS_OK;
+    explicit UploadSink(ns_index* i) : idx(i) {}
+    uint8_t* begin(uint64_t P) override {
+        rc = ns_upload_begin(idx, P, &up);
+        return rc == NS_OK ? (uint8_t*)ns_upload_buffer(up) : nullptr;
+    }
+    void filled(uint64_t first, uint64_t count) override { ns_upload_push(up, first, count); }
+    ~UploadSink() override {
+        if (up) ns_upload_abort(up);
+    }
+};
+
+int do_reload(ns_engine* e) {
+    using clk = std::chrono::steady_clock;
+    const auto t0 = clk::now();
+    auto g = std::make_shared<Generation>();
+    g->seg_names = discover_segments(e->index_dir);
+    if (g->seg_names.empty()) { set_error("no segments under " + e->index_dir); return NS_ERR_IO; }  // src/api_engine.cpp:73
+    const size_t nseg = g->seg_names.size();
+    const int ndev = (int)e->devices.size();
+    g->segs.resize(nseg);
+    g->seg_dev.assign(nseg, -1);
+    g->dev_cols.resize((size_t)std::max(1, ndev));
+    auto abort_all = [&]() {
+        for (auto* ix : e->idx) ns_index_abort(ix);
+    };
+    const int nt = hw_threads();
+    uint32_t owned_j = 0;
+    double read_s = 0;
+    for (size_t i = 0; i < nseg; i++) {
+        if (!e->owns(i)) continue;
+        const int d = ndev ? (int)(owned_j % (uint32_t)ndev) : -1;
+        g->seg_dev[i] = d;
+        g->dev_cols[(size_t)std::max(0, d)].push_back(owned_j);
+        owned_j++;
+        auto seg = std::make_unique<HostSegment>();
+        const std::string dir = e->index_dir + "/segments/" + g->seg_names[i];
+        const auto r0 = clk::now();
+        if (d < 0) {
+            if (!load_segment(dir, *seg, nt)) return NS_ERR_IO;
+            seg->drop_postings();  // a host-only engine resolves queries; it never scores
+        } else {
+            UploadSink sink(e->idx[(size_t)d]);
+            if (!load_segment(dir, *seg, nt, &sink)) {
+                abort_all();
+                return sink.rc != NS_OK ? sink.rc : NS_ERR_IO;  // reference: reload() returns false, old segments stay (:82-85)
+            }
+            read_s += std::chrono::duration<double>(clk::now() - r0).count();
+            std::vector<uint64_t> begin(seg->rows.size());
+            std::vector<uint32_t> count(seg->rows.size());
+            std::vector<float> idf(seg->rows.size());
+            for (size_t r = 0; r < seg->rows.size(); r++) {
+                begin[r] = seg->rows[r].begin;
+                count[r] = seg->rows[r].count;
+                idf[r] = seg->rows[r].idf;  // bm25_idf(N, df): the resident scores are built with what queries will ask for
+            }
+            ns_upload* up = sink.up;
+            sink.up = nullptr;  // finish frees the ticket
+            if (!up) {
+                abort_all();
+                set_error("segment loader did not open an upload for " + dir);
+                return NS_ERR_STATE;
+            }
+            int rc = ns_upload_finish(up, (uint32_t)i, (uint32_t)seg->doc_len.size(), seg->avgdl, seg->doc_len.data(),
+                                      (uint32_t)seg->rows.size(), begin.data(), count.data(), idf.data(),
+                                      e->keep_raw ? 0u : NS_SEG_DROP_RAW);
+            if (rc != NS_OK) {
+                abort_all();
+                return rc;
+            }
+            for (auto& r : seg->rows) g->posting_bytes += 8ull * r.count;
+        }
+        g->segs[i] = std::move(seg);
+    }
+    for (auto* ix : e->idx) {
+        int rc = ns_index_commit(ix);
+        if (rc != NS_OK) {
+            abort_all();
+            return rc;
         }
     }
+    for (auto* ix : e->idx) g->dev_state.push_back(index_live_state(ix));
+    const auto t1 = clk::now();
+    g->dict.build(g->segs);
+    const auto t2 = clk::now();
+    // result decoration and semantic expansion data (src/api_engine.cpp:110-152)
+    g->meta.load(e->index_dir + "/metadata.csv");
+    {
+        std::string emb;
+        if (const char* p = std::getenv("EMBEDDINGS_PATH")) emb = p;
+        else
+            for (const char* nm : {"embeddings.vec", "embeddings.txt", "glove.txt", "vectors.txt"})
+                if (emb.empty() && file_exists(e->index_dir + "/" + nm)) emb = e->index_dir + "/" + nm;
+        if (!emb.empty() && file_exists(emb)) {
+            const TermDict& dict = g->dict;
+            g->sem.load(emb, [&](const std::string& w) { return dict.find(w.data(), w.size(), term_hash(w.data(), w.size())) >= 0; });
+        }
+    }
+    e->last_reload.total_s = std::chrono::duration<double>(clk::now() - t0).count();
+    e->last_reload.read_s = read_s;
+    e->last_reload.dict_s = std::chrono::duration<double>(t2 - t1).count();
+    e->last_reload.posting_bytes = g->posting_bytes;
+    std::lock_guard<std::mutex> lk(e->gen_mu);
+    e->gen = g;  // in-flight calls keep the generation they started with
+    return NS_OK;
 }
 
-// shortest round-trip decimal of the f32 score widened to double (r["score"] = h.s,
-// src/api_engine.cpp:511), with ".0" appended to integral values like nlohmann::json::dump
-void json_double(double v, std::string& out) {
-    char buf[64];
-    auto res = std::to_chars(buf, buf + sizeof(buf), v);
-    std::string s(buf, res.ptr);
-    if (s.find_first_of(".eEn") == std::string::npos) s += ".0";
-    out += s;
-}
+// ------------------------------------------------------------------------------------------
+// front end: query text -> (segment, row, idf, weight) tuples, once per batch
+// ------------------------------------------------------------------------------------------
 
-// Resolve one query against the owned segments.  Emits terms ordered by (segment asc, query order).
-// Returns whether the reference would compute "found" (base_terms and segments non-empty).
-bool resolve_one(const ns_engine* e, const char* query, std::vector<ns_qterm>& out) {
+struct QueryTerm {
+    uint32_t gid;  // dictionary id
+    float w;
+};
+
+// Terms of one query in scoring order.  Plain search: the tokens that survive the filter, weight 1.0f
+// (src/api_engine.cpp:388-397, 418-421).  With embeddings: SemanticIndex::expand's list (:410-417).
+// Returns whether the reference would compute "found" (:407, :424).
+bool query_terms_of(const Generation& g, const char* query, std::vector<QueryTerm>& out) {
     static thread_local std::string buf;
     static thread_local std::vector<TokSpan> spans;
-    static thread_local std::vector<uint64_t> hashes;
+    out.clear();
     query_term_spans(query, buf, spans);
-    if (spans.empty() || e->seg_names.empty()) return false;  // src/api_engine.cpp:407
-    hashes.resize(spans.size());
-    for (size_t i = 0; i < spans.size(); i++) hashes[i] = term_hash(buf.data() + spans[i].off, spans[i].len);  // once per token
-    for (size_t si = 0; si < e->segs.size(); si++) {
-        const HostSegment* seg = e->segs[si].get();
-        if (!seg) continue;
-        for (size_t i = 0; i < spans.size(); i++) {  // qweight 1.0f: src/api_engine.cpp:420
-            const int64_t row = seg->table.find(buf.data() + spans[i].off, spans[i].len, hashes[i]);
-            if (row < 0) continue;  // :454-455
-            const LexRow& r = seg->rows[(size_t)row];
-            if (r.df == 0) continue;  // :458
-            out.push_back(ns_qterm{(uint32_t)si, (uint32_t)row, r.idf, 1.0f});
+    if (spans.empty() || g.seg_names.empty()) return false;
+    if (!g.sem.enabled) {
+        for (const TokSpan& s : spans) {
+            const char* p = buf.data() + s.off;
+            const int64_t gid = g.dict.find(p, s.len, term_hash(p, s.len));
+            if (gid >= 0) out.push_back(QueryTerm{(uint32_t)gid, 1.0f});
         }
+        return true;
+    }
+    std::vector<std::string> base;
+    base.reserve(spans.size());
+    for (const TokSpan& s : spans) base.emplace_back(buf.data() + s.off, s.len);
+    const auto qw = g.sem.expand(base);
+    if (qw.empty()) return false;
+    for (const auto& tw : qw) {
+        const int64_t gid = g.dict.find(tw.first.data(), tw.first.size(), term_hash(tw.first.data(), tw.first.size()));
+        if (gid >= 0) out.push_back(QueryTerm{(uint32_t)gid, tw.second});
     }
     return true;
 }
 
-}  // namespace
-
-extern "C" int ns_engine_create(const char* index_dir, int device, ns_engine** out) {
-    if (!index_dir || !out) { set_error("ns_engine_create: null argument"); return NS_ERR_INVALID; }
-    *out = nullptr;
-    auto e = std::make_unique<ns_engine>();
-    e->index_dir = index_dir;
-    e->device = device;
-    if (device >= 0) {
-        int rc = ns_index_create(device, &e->idx);
-        if (rc != NS_OK) return rc;
-    }
-    *out = e.release();
-    return NS_OK;
-}
-
-extern "C" void ns_engine_destroy(ns_engine* e) {
-    if (!e) return;
-    if (e->idx) ns_index_destroy(e->idx);
-    delete e;
-}
-
-extern "C" int ns_engine_set_shard(ns_engine* e, int rank, int world) {
-    if (!e || world < 1 || rank < 0 || rank >= world) { set_error("ns_engine_set_shard: bad rank/world"); return NS_ERR_INVALID; }
-    std::unique_lock<std::shared_mutex> lk(e->mu);
-    e->rank = rank;
-    e->world = world;
-    return NS_OK;
-}
-
-extern "C" int ns_engine_reload(ns_engine* e) {
-    if (!e) { set_error("ns_engine_reload: null"); return NS_ERR_INVALID; }
-    std::unique_lock<std::shared_mutex> lk(e->mu);
-    std::vector<std::string> names = discover_segments(e->index_dir);
-    if (names.empty()) { set_error("no segments under " + e->index_dir); return NS_ERR_IO; }  // :73
-    std::vector<std::unique_ptr<HostSegment>> loaded(names.size());
-    const int nt = hw_threads();
-    for (size_t i = 0; i < names.size(); i++) {
-        if ((int)(i % (size_t)e->world) != e->rank) continue;
-        auto seg = std::make_unique<HostSegment>();
-        if (!load_segment(e->index_dir + "/segments/" + names[i], *seg, nt)) {
-            if (e->idx) ns_index_abort(e->idx);
-            return NS_ERR_IO;  // reference: reload() returns false, old segments stay (:82-85)
-        }
-        if (e->idx) {
-            std::vector<uint64_t> begin(seg->rows.size());
-            std::vector<uint32_t> count(seg->rows.size());
-            for (size_t r = 0; r < seg->rows.size(); r++) {
-                begin[r] = seg->rows[r].begin;
-                count[r] = seg->rows[r].count;
-            }
-            int rc = ns_index_add_segment(e->idx, (uint32_t)i, (uint32_t)seg->doc_len.size(), seg->avgdl,
-                                          seg->doc_len.data(), (uint32_t)seg->rows.size(), begin.data(), count.data(),
-                                          seg->postings.data(), seg->postings.size());
-            if (rc != NS_OK) {
-                ns_index_abort(e->idx);
-                return rc;
-            }
-            seg->drop_postings();  // they live in HBM now
-        }
-        loaded[i] = std::move(seg);
-    }
-    if (e->idx) {
-        int rc = ns_index_commit(e->idx);
-        if (rc != NS_OK) {
-            ns_index_abort(e->idx);
-            return rc;
+// Emit the query's terms for the dictionary columns `cols` (ascending segments): ordered by
+// (segment asc, query-term order), duplicates kept (:391-397, :449).
+inline void emit_terms(const Generation& g, const std::vector<QueryTerm>& qt, const std::vector<uint32_t>& cols,
+                       std::vector<ns_qterm>& out) {
+    const size_t ncol = g.dict.owned.size();
+    for (uint32_t j : cols) {
+        const uint32_t seg = g.dict.owned[j];
+        for (const QueryTerm& t : qt) {
+            const TermDict::Entry& en = g.dict.table[(size_t)t.gid * ncol + j];
+            if (en.row == TermDict::kAbsent) continue;  // :454-458
+            out.push_back(ns_qterm{seg, en.row, en.idf, t.w});
         }
     }
-    e->seg_names = std::move(names);
-    e->segs = std::move(loaded);
-    return NS_OK;
 }
 
-extern "C" int ns_engine_num_segments(const ns_engine* e) {
-    if (!e) return 0;
-    std::shared_lock<std::shared_mutex> lk(e->mu);
-    return (int)e->seg_names.size();
-}
-
-extern "C" int ns_engine_segment_name(const ns_engine* e, int i, char* buf, size_t cap) {
-    if (!e || !buf) return -1;
-    std::shared_lock<std::shared_mutex> lk(e->mu);
-    if (i < 0 || (size_t)i >= e->seg_names.size()) return -1;
-    const std::string& s = e->seg_names[i];
-    if (s.size() + 1 > cap) return -1;
-    std::memcpy(buf, s.c_str(), s.size() + 1);
-    return (int)s.size();
-}
-
-extern "C" int ns_engine_segment_stats(const ns_engine* e, int i, uint32_t* N, float* avgdl, uint32_t* T, uint64_t* P) {
-    if (!e) return NS_ERR_INVALID;
-    std::shared_lock<std::shared_mutex> lk(e->mu);
-    if (i < 0 || (size_t)i >= e->segs.size() || !e->segs[i]) { set_error("segment not loaded by this engine"); return NS_ERR_INVALID; }
-    const HostSegment& s = *e->segs[i];
-    if (N) *N = s.N;
-    if (avgdl) *avgdl = s.avgdl;
-    if (T) *T = (uint32_t)s.rows.size();
-    if (P) {
-        uint64_t p = 0;
-        for (auto& r : s.rows) p += r.count;
-        *P = p;
-    }
-    return NS_OK;
-}
-
-extern "C" int ns_engine_term_stats(const ns_engine* e, int i, const char* term, uint32_t* df, uint32_t* count) {
-    if (df) *df = 0;
-    if (count) *count = 0;
-    if (!e || !term) return NS_ERR_INVALID;
-    std::shared_lock<std::shared_mutex> lk(e->mu);
-    if (i < 0 || (size_t)i >= e->segs.size() || !e->segs[i]) { set_error("segment not loaded by this engine"); return NS_ERR_INVALID; }
-    auto it = e->segs[i]->lex.find(term);
-    if (it == e->segs[i]->lex.end()) return NS_OK;
-    if (df) *df = e->segs[i]->rows[it->second].df;
-    if (count) *count = e->segs[i]->rows[it->second].count;
-    return NS_OK;
-}
-
-extern "C" ns_index* ns_engine_index(ns_engine* e) { return e ? e->idx : nullptr; }
-
-extern "C" int ns_engine_cord_uid(const ns_engine* e, uint32_t seg, uint32_t doc, char* buf, size_t cap) {
-    if (!e || !buf) return -1;
-    std::shared_lock<std::shared_mutex> lk(e->mu);
-    if (seg >= e->segs.size() || !e->segs[seg]) return -1;
-    std::string s = e->segs[seg]->cord_uid(doc);
-    if (s.size() + 1 > cap) return -1;
-    std::memcpy(buf, s.c_str(), s.size() + 1);
-    return (int)s.size();
-}
-
-namespace {
-
-// One pass over the batch: tokenise, filter, look every term up in every owned segment's lexicon.
-// The queries are independent, so the batch is cut into contiguous ranges, one per host thread
-// (the reference serialises whole searches on Engine::mtx, src/api_engine.cpp:372).
 struct Resolved {
-    std::vector<uint64_t> q_off;   // [Q+1]
+    std::vector<uint64_t> q_off;  // [Q+1]
     std::vector<ns_qterm> terms;
-    std::vector<uint8_t> has;      // [Q]
 };
 
-template <class GetQuery>
-void resolve_all(ns_engine* e, uint32_t Q, GetQuery get, Resolved& out) {
-    std::call_once(e->pool_once, [&] { e->pool.reset(new WorkPool(std::max(0, std::min(hw_threads(), 8) - 1))); });
-    static const int max_nt = std::getenv("NSB200_HOST_THREADS") ? std::atoi(std::getenv("NSB200_HOST_THREADS")) : 1 << 20;
-    // a sharded engine is one of `world` processes on the same box: take a 1/world share of the cores
-    const int share = std::max(1, hw_threads() / std::max(1, e->world));
-    const int nt = std::max(1, std::min(std::min(std::min(e->pool->workers() + 1, max_nt), share), (int)(Q / 256) + 1));
-    std::vector<std::vector<ns_qterm>> per((size_t)nt);
-    std::vector<uint32_t> cnt(Q, 0);
-    out.has.assign(Q, 0);
+// One pass over the batch on the engine's host threads.  parts[p] receives the terms of the dictionary
+// columns colsets[p] (one part per device, or a single part with every owned segment).
+template <class TermsOf>
+void resolve_all(ns_engine* e, const Generation& g, uint32_t Q, TermsOf terms_of,
+                 const std::vector<const std::vector<uint32_t>*>& colsets, std::vector<Resolved>& parts,
+                 std::vector<uint8_t>& has) {
+    const size_t np = colsets.size();
+    WorkPool& pool = e->workers();
+    const int nt = std::max(1, std::min(pool.workers() + 1, (int)(Q / 128) + 1));
+    std::vector<std::vector<std::vector<ns_qterm>>> per((size_t)nt, std::vector<std::vector<ns_qterm>>(np));
+    std::vector<std::vector<uint32_t>> cnt(np, std::vector<uint32_t>(Q, 0));
+    has.assign(Q, 0);
     auto lo_of = [&](int t) { return (uint32_t)((uint64_t)Q * t / nt); };
     auto work = [&](int t) {
-        per[t].reserve((size_t)(lo_of(t + 1) - lo_of(t)) * 4);
+        std::vector<QueryTerm> qt;
+        for (size_t p = 0; p < np; p++) per[t][p].reserve((size_t)(lo_of(t + 1) - lo_of(t)) * 4);
         for (uint32_t q = lo_of(t); q < lo_of(t + 1); q++) {
-            const size_t before = per[t].size();
-            out.has[q] = resolve_one(e, get(q), per[t]) ? 1 : 0;
-            cnt[q] = (uint32_t)(per[t].size() - before);
+            has[q] = terms_of(q, qt) ? 1 : 0;
+            for (size_t p = 0; p < np; p++) {
+                const size_t before = per[t][p].size();
+                emit_terms(g, qt, *colsets[p], per[t][p]);
+                cnt[p][q] = (uint32_t)(per[t][p].size() - before);
+            }
         }
     };
-    e->pool->run(nt, work);
-    out.q_off.resize((size_t)Q + 1);
-    uint64_t total = 0;
-    out.q_off[0] = 0;
-    for (uint32_t q = 0; q < Q; q++) {
-        total += cnt[q];
-        out.q_off[q + 1] = total;
-    }
-    out.terms.resize(std::max<uint64_t>(1, total));
-    uint64_t at = 0;
-    for (int t = 0; t < nt; t++) {
-        if (!per[t].empty()) std::memcpy(out.terms.data() + at, per[t].data(), per[t].size() * sizeof(ns_qterm));
-        at += per[t].size();
+    pool.run(nt, work);
+    parts.assign(np, Resolved{});
+    for (size_t p = 0; p < np; p++) {
+        Resolved& r = parts[p];
+        r.q_off.resize((size_t)Q + 1);
+        uint64_t total = 0;
+        r.q_off[0] = 0;
+        for (uint32_t q = 0; q < Q; q++) {
+            total += cnt[p][q];
+            r.q_off[q + 1] = total;
+        }
+        r.terms.resize(std::max<uint64_t>(1, total));
+        uint64_t at = 0;
+        for (int t = 0; t < nt; t++) {
+            if (!per[t][p].empty()) std::memcpy(r.terms.data() + at, per[t][p].data(), per[t][p].size() * sizeof(ns_qterm));
+            at += per[t][p].size();
+        }
     }
 }
 
@@ -293,22 +350,420 @@ bool split_packed(const char* z, size_t nbytes, uint32_t Q, std::vector<const ch
     return true;
 }
 
+// ------------------------------------------------------------------------------------------
+// scoring: one device, or all devices + peer exchange
+// ------------------------------------------------------------------------------------------
+
+int acquire_group(ns_engine* e, uint32_t Q, std::unique_ptr<XGroup>& out) {
+    {
+        std::lock_guard<std::mutex> lk(e->xg_mu);
+        for (size_t i = 0; i < e->xg_pool.size(); i++) {
+            if (e->xg_pool[i]->max_q >= Q) {
+                out = std::move(e->xg_pool[i]);
+                e->xg_pool.erase(e->xg_pool.begin() + (long)i);
+                return NS_OK;
+            }
+        }
+    }
+    auto g = std::make_unique<XGroup>();
+    uint32_t cap = 4096;
+    while (cap < Q) cap <<= 1;
+    g->max_q = cap;
+    const uint32_t ndev = (uint32_t)e->devices.size();
+    g->x.assign(ndev, nullptr);
+    for (uint32_t d = 0; d < ndev; d++) {
+        int rc = ns_exchange_create(e->devices[d], ndev, d, cap, 1, &g->x[d]);
+        if (rc != NS_OK) return rc;
+    }
+    for (uint32_t d = 0; d < ndev; d++) {  // everybody publishes into the root's gather buffer; the root receives
+        int rc = ns_exchange_attach_local(g->x[d], g->x[0]);
+        if (rc != NS_OK) return rc;
+    }
+    out = std::move(g);
+    return NS_OK;
+}
+
+void release_group(ns_engine* e, std::unique_ptr<XGroup> g) {
+    std::lock_guard<std::mutex> lk(e->xg_mu);
+    if (e->xg_pool.size() < 16) e->xg_pool.push_back(std::move(g));
+}
+
+template <class TermsOf>
+int search_core(ns_engine* e, const std::shared_ptr<const Generation>& gen, uint32_t Q, TermsOf terms_of, int k,
+                ns_hit* out_hits, uint32_t* out_nhits, uint64_t* out_found, uint8_t* has_found) {
+    if (e->idx.empty()) { set_error("engine was created without a CUDA device; there is no CPU search path"); return NS_ERR_STATE; }
+    if (!gen) { set_error("search before a successful reload"); return NS_ERR_STATE; }
+    const Generation& g = *gen;
+    const size_t ndev = e->idx.size();
+    std::vector<const std::vector<uint32_t>*> colsets;
+    for (size_t d = 0; d < ndev; d++) colsets.push_back(&g.dev_cols[d]);
+    std::vector<Resolved> parts;
+    std::vector<uint8_t> has;
+    resolve_all(e, g, Q, terms_of, colsets, parts, has);
+    if (has_found && Q) std::memcpy(has_found, has.data(), Q);
+
+    if (ndev == 1) {
+        ns_batch* b = nullptr;
+        int rc = batch_prepare_on(e->idx[0], g.dev_state[0], Q, k, parts[0].q_off.data(), parts[0].terms.data(), &b);
+        if (rc != NS_OK) return rc;
+        rc = ns_batch_launch(b, nullptr);
+        if (rc == NS_OK) rc = ns_batch_fetch(b, out_hits, out_nhits, out_found);
+        ns_batch_destroy(b);
+        return rc;
+    }
+
+    // several devices: prepare + launch on every device in parallel; each score kernel stores its per-query
+    // results into the root's gather buffer; the root merges once all score kernels are done.
+    std::unique_ptr<XGroup> grp;
+    int rc = acquire_group(e, std::max<uint32_t>(1, Q), grp);
+    if (rc != NS_OK) return rc;
+    const uint64_t step = grp->step++;
+    std::vector<ns_batch*> bs(ndev, nullptr);
+    std::vector<int> rcs(ndev, NS_OK);
+    std::vector<std::string> errs(ndev);
+    auto one = [&](int d) {
+        rcs[d] = batch_prepare_on(e->idx[d], g.dev_state[d], Q, k, parts[d].q_off.data(), parts[d].terms.data(), &bs[d]);
+        if (rcs[d] == NS_OK) rcs[d] = ns_batch_launch_exchange(bs[d], grp->x[d], step, nullptr);
+        if (rcs[d] != NS_OK) errs[d] = ns_last_error();
+    };
+    e->workers().run((int)ndev, one);
+    for (size_t d = 0; d < ndev && rc == NS_OK; d++)
+        if (rcs[d] != NS_OK) {
+            rc = rcs[d];
+            set_error(errs[d]);
+        }
+    if (rc == NS_OK) rc = exchange_root_merge(grp->x[0], bs.data(), (int)ndev, step, Q, k);
+    if (rc == NS_OK) rc = ns_exchange_fetch(grp->x[0], step, Q, k, out_hits, out_nhits, out_found);
+    std::string keep = rc != NS_OK ? std::string(ns_last_error()) : std::string();
+    for (auto* b : bs)
+        if (b) ns_batch_destroy(b);  // waits for that device's kernels
+    if (rc == NS_OK) release_group(e, std::move(grp));  // a failed group is dropped: its flags may be in any state
+    else set_error(keep);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------
+// request coalescing: many threads each with ONE query -> GPU-sized batches
+// ------------------------------------------------------------------------------------------
+
+struct Coalescer {
+    struct Req {
+        const char* query;
+        int k;
+        ns_hit* hits;
+        uint32_t* nhits;
+        uint64_t* found;
+        uint8_t* has;
+        std::shared_ptr<const Generation>* gen_out;
+        int rc = NS_OK;
+        std::string err;
+        bool done = false;
+        std::chrono::steady_clock::time_point t_in;
+    };
+    ns_engine* e;
+    uint32_t max_batch, max_wait_us;
+    std::mutex mu;
+    std::condition_variable cv_work, cv_done;
+    std::deque<Req*> queue;
+    bool stop = false;
+    std::vector<std::thread> th;
+    std::atomic<uint64_t> n_batches{0}, n_queries{0}, max_seen{0};
+
+    Coalescer(ns_engine* eng, uint32_t mb, uint32_t mw, int dispatchers) : e(eng), max_batch(std::max(1u, mb)), max_wait_us(mw) {
+        for (int i = 0; i < std::max(1, dispatchers); i++) th.emplace_back([this] { loop(); });
+    }
+    ~Coalescer() {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            stop = true;
+        }
+        cv_work.notify_all();
+        for (auto& t : th) t.join();
+    }
+    int submit_and_wait(Req& r) {
+        r.t_in = std::chrono::steady_clock::now();
+        std::unique_lock<std::mutex> lk(mu);
+        if (stop) { set_error("coalescer is stopping"); return NS_ERR_STATE; }
+        queue.push_back(&r);
+        if (queue.size() == 1 || queue.size() >= max_batch) cv_work.notify_one();
+        cv_done.wait(lk, [&] { return r.done; });
+        if (r.rc != NS_OK) set_error(r.err);
+        return r.rc;
+    }
+    void loop();
+};
+
+void Coalescer::loop() {
+    std::vector<Req*> take;
+    for (;;) {
+        take.clear();
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv_work.wait(lk, [&] { return stop || !queue.empty(); });
+            if (queue.empty()) {
+                if (stop) return;
+                continue;
+            }
+            // gather: until the batch is full or the oldest request has waited max_wait_us
+            const auto deadline = queue.front()->t_in + std::chrono::microseconds(max_wait_us);
+            while (!stop && !queue.empty() && queue.size() < max_batch && std::chrono::steady_clock::now() < deadline)
+                cv_work.wait_until(lk, deadline);
+            if (queue.empty()) continue;  // another dispatcher took the requests while this one was gathering
+            // one batch = requests of one k class (k <= 16 and k > 16 run different kernel variants)
+            const bool big = queue.front()->k > 16;
+            for (auto it = queue.begin(); it != queue.end() && take.size() < max_batch;) {
+                if (((*it)->k > 16) == big) {
+                    take.push_back(*it);
+                    it = queue.erase(it);
+                } else {
+                    ++it;
+                }
+            }
+            if (!queue.empty()) cv_work.notify_one();  // another dispatcher may start on the rest
+        }
+        const uint32_t Q = (uint32_t)take.size();
+        int K = 1;
+        for (Req* r : take) K = std::max(K, std::max(1, std::min(r->k, NS_MAX_K)));
+        std::vector<ns_hit> hits((size_t)Q * K);
+        std::vector<uint32_t> nh(Q);
+        std::vector<uint64_t> fo(Q);
+        std::vector<uint8_t> has(Q);
+        auto gen = e->snapshot();
+        int rc = NS_ERR_STATE;
+        std::string err = "search before a successful reload";
+        if (gen) {
+            const Generation& g = *gen;
+            rc = search_core(e, gen, Q, [&](uint32_t q, std::vector<QueryTerm>& qt) { return query_terms_of(g, take[q]->query, qt); },
+                             K, hits.data(), nh.data(), fo.data(), has.data());
+            if (rc != NS_OK) err = ns_last_error();
+        }
+        n_batches++;
+        n_queries += Q;
+        uint64_t seen = max_seen.load();
+        while (Q > seen && !max_seen.compare_exchange_weak(seen, Q)) {}
+        for (uint32_t q = 0; q < Q; q++) {
+            Req* r = take[q];
+            r->rc = rc;
+            if (rc == NS_OK) {
+                // the first k' entries of a top-K list are the top-k' list (total order): cut to the caller's k
+                const uint32_t kr = (uint32_t)std::max(1, std::min(r->k, NS_MAX_K));
+                const uint32_t n = std::min(nh[q], kr);
+                if (r->hits && n) std::memcpy(r->hits, hits.data() + (size_t)q * K, (size_t)n * sizeof(ns_hit));
+                if (r->nhits) *r->nhits = n;
+                if (r->found) *r->found = fo[q];
+                if (r->has) *r->has = has[q];
+                if (r->gen_out) *r->gen_out = gen;
+            } else {
+                r->err = err;
+            }
+        }
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            for (Req* r : take) r->done = true;
+        }
+        cv_done.notify_all();
+    }
+}
+
+// one query, through the coalescer when it runs; gen_out receives the generation the answer came from
+int search_one(ns_engine* e, const char* query, int k, ns_hit* hits, uint32_t* nhits, uint64_t* found, uint8_t* has,
+               std::shared_ptr<const Generation>* gen_out) {
+    Coalescer* co = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(e->co_mu);
+        co = e->coalescer.get();
+    }
+    if (co) {
+        Coalescer::Req r;
+        r.query = query;
+        r.k = k;
+        r.hits = hits;
+        r.nhits = nhits;
+        r.found = found;
+        r.has = has;
+        r.gen_out = gen_out;
+        return co->submit_and_wait(r);
+    }
+    auto gen = e->snapshot();
+    if (gen_out) *gen_out = gen;
+    if (!gen) { set_error("search before a successful reload"); return e->idx.empty() ? NS_ERR_STATE : NS_ERR_STATE; }
+    const Generation& g = *gen;
+    return search_core(e, gen, 1, [&](uint32_t, std::vector<QueryTerm>& qt) { return query_terms_of(g, query, qt); }, k, hits,
+                       nhits, found, has);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+
+extern "C" int ns_engine_create_multi(const char* index_dir, int ndev, const int* devices, ns_engine** out) {
+    if (!index_dir || !out || ndev < 0 || (ndev > 0 && !devices) || ndev > NS_MAX_PEERS) {
+        set_error("ns_engine_create_multi: bad argument");
+        return NS_ERR_INVALID;
+    }
+    *out = nullptr;
+    auto e = std::make_unique<ns_engine>();
+    e->index_dir = index_dir;
+    e->keep_raw = std::getenv("NSB200_KEEP_RAW") != nullptr;
+    for (int d = 0; d < ndev; d++) {
+        // (the same ordinal may be listed more than once: two device slots on one GPU — how the
+        //  multi-device path is exercised on a single-GPU box)
+        ns_index* ix = nullptr;
+        if (ns_index_create(devices[d], &ix) != NS_OK) goto fail_cuda;
+        e->idx.push_back(ix);
+        e->devices.push_back(devices[d]);
+    }
+    *out = e.release();
+    return NS_OK;
+fail_cuda:
+    for (auto* ix : e->idx) ns_index_destroy(ix);
+    return NS_ERR_CUDA;
+}
+
+extern "C" int ns_engine_create(const char* index_dir, int device, ns_engine** out) {
+    if (device < 0) return ns_engine_create_multi(index_dir, 0, nullptr, out);
+    return ns_engine_create_multi(index_dir, 1, &device, out);
+}
+
+extern "C" void ns_engine_destroy(ns_engine* e) {
+    if (!e) return;
+    {
+        std::lock_guard<std::mutex> lk(e->co_mu);
+        e->coalescer.reset();  // drains and joins the dispatchers
+    }
+    e->xg_pool.clear();
+    {
+        std::lock_guard<std::mutex> lk(e->gen_mu);
+        e->gen.reset();
+    }
+    for (auto* ix : e->idx) ns_index_destroy(ix);
+    delete e;
+}
+
+extern "C" int ns_engine_num_devices(const ns_engine* e) { return e ? (int)e->devices.size() : 0; }
+
+extern "C" int ns_engine_set_shard(ns_engine* e, int rank, int world) {
+    if (!e || world < 1 || rank < 0 || rank >= world) { set_error("ns_engine_set_shard: bad rank/world"); return NS_ERR_INVALID; }
+    std::lock_guard<std::mutex> lk(e->reload_mu);
+    e->rank = rank;
+    e->world = world;
+    return NS_OK;
+}
+
+extern "C" int ns_engine_reload(ns_engine* e) {
+    if (!e) { set_error("ns_engine_reload: null"); return NS_ERR_INVALID; }
+    std::lock_guard<std::mutex> lk(e->reload_mu);
+    return do_reload(e);
+}
+
+extern "C" int ns_engine_reload_stats(const ns_engine* e, double* total_s, double* read_upload_s, double* dict_s,
+                                      uint64_t* posting_bytes, uint64_t* device_bytes) {
+    if (!e) return NS_ERR_INVALID;
+    if (total_s) *total_s = e->last_reload.total_s;
+    if (read_upload_s) *read_upload_s = e->last_reload.read_s;
+    if (dict_s) *dict_s = e->last_reload.dict_s;
+    if (posting_bytes) *posting_bytes = e->last_reload.posting_bytes;
+    if (device_bytes) {
+        uint64_t b = 0;
+        for (auto* ix : e->idx) b += ns_index_device_bytes(ix);
+        *device_bytes = b;
+    }
+    return NS_OK;
+}
+
+extern "C" int ns_engine_num_segments(const ns_engine* e) {
+    if (!e) return 0;
+    auto g = const_cast<ns_engine*>(e)->snapshot();
+    return g ? (int)g->seg_names.size() : 0;
+}
+
+extern "C" int ns_engine_segment_name(const ns_engine* e, int i, char* buf, size_t cap) {
+    if (!e || !buf) return -1;
+    auto g = const_cast<ns_engine*>(e)->snapshot();
+    if (!g || i < 0 || (size_t)i >= g->seg_names.size()) return -1;
+    const std::string& s = g->seg_names[(size_t)i];
+    if (s.size() + 1 > cap) return -1;
+    std::memcpy(buf, s.c_str(), s.size() + 1);
+    return (int)s.size();
+}
+
+extern "C" int ns_engine_segment_stats(const ns_engine* e, int i, uint32_t* N, float* avgdl, uint32_t* T, uint64_t* P) {
+    if (!e) return NS_ERR_INVALID;
+    auto g = const_cast<ns_engine*>(e)->snapshot();
+    if (!g || i < 0 || (size_t)i >= g->segs.size() || !g->segs[(size_t)i]) { set_error("segment not loaded by this engine"); return NS_ERR_INVALID; }
+    const HostSegment& s = *g->segs[(size_t)i];
+    if (N) *N = s.N;
+    if (avgdl) *avgdl = s.avgdl;
+    if (T) *T = (uint32_t)s.rows.size();
+    if (P) {
+        uint64_t p = 0;
+        for (auto& r : s.rows) p += r.count;
+        *P = p;
+    }
+    return NS_OK;
+}
+
+extern "C" int ns_engine_term_stats(const ns_engine* e, int i, const char* term, uint32_t* df, uint32_t* count) {
+    if (df) *df = 0;
+    if (count) *count = 0;
+    if (!e || !term) return NS_ERR_INVALID;
+    auto g = const_cast<ns_engine*>(e)->snapshot();
+    if (!g || i < 0 || (size_t)i >= g->segs.size() || !g->segs[(size_t)i]) { set_error("segment not loaded by this engine"); return NS_ERR_INVALID; }
+    auto it = g->segs[(size_t)i]->lex.find(term);
+    if (it == g->segs[(size_t)i]->lex.end()) return NS_OK;
+    if (df) *df = g->segs[(size_t)i]->rows[it->second].df;
+    if (count) *count = g->segs[(size_t)i]->rows[it->second].count;
+    return NS_OK;
+}
+
+extern "C" ns_index* ns_engine_index(ns_engine* e) { return e && !e->idx.empty() ? e->idx[0] : nullptr; }
+extern "C" ns_index* ns_engine_device_index(ns_engine* e, int slot) {
+    return e && slot >= 0 && (size_t)slot < e->idx.size() ? e->idx[(size_t)slot] : nullptr;
+}
+
+extern "C" int ns_engine_cord_uid(const ns_engine* e, uint32_t seg, uint32_t doc, char* buf, size_t cap) {
+    if (!e || !buf) return -1;
+    auto g = const_cast<ns_engine*>(e)->snapshot();
+    if (!g || seg >= g->segs.size() || !g->segs[seg]) return -1;
+    std::string s = g->segs[seg]->cord_uid(doc);
+    if (s.size() + 1 > cap) return -1;
+    std::memcpy(buf, s.c_str(), s.size() + 1);
+    return (int)s.size();
+}
+
+namespace {
+
+template <class GetQuery>
+int resolve_abi(ns_engine* e, uint32_t Q, GetQuery get, uint64_t* q_off, ns_qterm* terms, uint64_t terms_cap,
+                uint64_t* n_terms, uint8_t* has_terms) {
+    auto gen = e->snapshot();
+    if (!gen) { set_error("resolve before a successful reload"); return NS_ERR_STATE; }
+    const Generation& g = *gen;
+    std::vector<uint32_t> all(g.dict.owned.size());
+    for (size_t j = 0; j < all.size(); j++) all[j] = (uint32_t)j;
+    std::vector<const std::vector<uint32_t>*> colsets{&all};
+    std::vector<Resolved> parts;
+    std::vector<uint8_t> has;
+    resolve_all(e, g, Q, [&](uint32_t q, std::vector<QueryTerm>& qt) { return query_terms_of(g, get(q), qt); }, colsets, parts, has);
+    const Resolved& r = parts[0];
+    const uint64_t total = r.q_off[Q];
+    std::memcpy(q_off, r.q_off.data(), ((size_t)Q + 1) * sizeof(uint64_t));
+    *n_terms = total;
+    if (has_terms && Q) std::memcpy(has_terms, has.data(), Q);
+    if (!terms) return NS_OK;
+    if (terms_cap < total) { set_error("ns_engine_resolve_batch: terms buffer too small"); return NS_ERR_INVALID; }
+    if (total) std::memcpy(terms, r.terms.data(), total * sizeof(ns_qterm));
+    return NS_OK;
+}
+
 }  // namespace
 
 extern "C" int ns_engine_resolve_batch(ns_engine* e, uint32_t Q, const char* const* queries, uint64_t* q_off,
                                        ns_qterm* terms, uint64_t terms_cap, uint64_t* n_terms, uint8_t* has_terms) {
     if (!e || (Q && !queries) || !q_off || !n_terms) { set_error("ns_engine_resolve_batch: null argument"); return NS_ERR_INVALID; }
-    std::shared_lock<std::shared_mutex> lk(e->mu);
-    Resolved r;
-    resolve_all(e, Q, [&](uint32_t q) { return queries[q]; }, r);
-    const uint64_t total = r.q_off[Q];
-    std::memcpy(q_off, r.q_off.data(), ((size_t)Q + 1) * sizeof(uint64_t));
-    *n_terms = total;
-    if (has_terms && Q) std::memcpy(has_terms, r.has.data(), Q);
-    if (!terms) return NS_OK;
-    if (terms_cap < total) { set_error("ns_engine_resolve_batch: terms buffer too small"); return NS_ERR_INVALID; }
-    if (total) std::memcpy(terms, r.terms.data(), total * sizeof(ns_qterm));
-    return NS_OK;
+    return resolve_abi(e, Q, [&](uint32_t q) { return queries[q]; }, q_off, terms, terms_cap, n_terms, has_terms);
 }
 
 extern "C" int ns_engine_resolve_batch_packed(ns_engine* e, uint32_t Q, const char* zqueries, size_t nbytes,
@@ -320,86 +775,185 @@ extern "C" int ns_engine_resolve_batch_packed(ns_engine* e, uint32_t Q, const ch
         set_error("ns_engine_resolve_batch_packed: buffer holds fewer than Q NUL-terminated strings");
         return NS_ERR_INVALID;
     }
-    std::shared_lock<std::shared_mutex> lk(e->mu);
-    Resolved r;
-    resolve_all(e, Q, [&](uint32_t q) { return starts[q]; }, r);
-    const uint64_t total = r.q_off[Q];
-    std::memcpy(q_off, r.q_off.data(), ((size_t)Q + 1) * sizeof(uint64_t));
-    *n_terms = total;
-    if (has_terms && Q) std::memcpy(has_terms, r.has.data(), Q);
-    if (!terms) return NS_OK;
-    if (terms_cap < total) { set_error("ns_engine_resolve_batch_packed: terms buffer too small"); return NS_ERR_INVALID; }
-    if (total) std::memcpy(terms, r.terms.data(), total * sizeof(ns_qterm));
-    return NS_OK;
+    return resolve_abi(e, Q, [&](uint32_t q) { return starts[q]; }, q_off, terms, terms_cap, n_terms, has_terms);
 }
 
 extern "C" int ns_engine_search_batch(ns_engine* e, uint32_t Q, const char* const* queries, int k, ns_hit* out_hits,
                                       uint32_t* out_nhits, uint64_t* out_found, uint8_t* has_found) {
     if (!e || (Q && !queries)) { set_error("ns_engine_search_batch: null argument"); return NS_ERR_INVALID; }
-    if (!e->idx) { set_error("engine was created without a CUDA device; there is no CPU search path"); return NS_ERR_STATE; }
-    Resolved r;
-    {
-        std::shared_lock<std::shared_mutex> lk(e->mu);
-        resolve_all(e, Q, [&](uint32_t q) { return queries[q]; }, r);
-    }
-    if (has_found && Q) std::memcpy(has_found, r.has.data(), Q);
-    return ns_search_batch(e->idx, Q, k, r.q_off.data(), r.terms.data(), out_hits, out_nhits, out_found);
+    auto gen = e->snapshot();
+    if (e->idx.empty()) { set_error("engine was created without a CUDA device; there is no CPU search path"); return NS_ERR_STATE; }
+    if (!gen) { set_error("search before a successful reload"); return NS_ERR_STATE; }
+    const Generation& g = *gen;
+    return search_core(e, gen, Q, [&](uint32_t q, std::vector<QueryTerm>& qt) { return query_terms_of(g, queries[q], qt); }, k,
+                       out_hits, out_nhits, out_found, has_found);
 }
 
 extern "C" int ns_engine_search_batch_packed(ns_engine* e, uint32_t Q, const char* zqueries, size_t nbytes, int k,
                                              ns_hit* out_hits, uint32_t* out_nhits, uint64_t* out_found,
                                              uint8_t* has_found) {
     if (!e || (Q && !zqueries)) { set_error("ns_engine_search_batch_packed: null argument"); return NS_ERR_INVALID; }
-    if (!e->idx) { set_error("engine was created without a CUDA device; there is no CPU search path"); return NS_ERR_STATE; }
+    if (e->idx.empty()) { set_error("engine was created without a CUDA device; there is no CPU search path"); return NS_ERR_STATE; }
     std::vector<const char*> starts;
     if (!split_packed(zqueries, nbytes, Q, starts)) {
         set_error("ns_engine_search_batch_packed: buffer holds fewer than Q NUL-terminated strings");
         return NS_ERR_INVALID;
     }
-    Resolved r;
-    static const bool trace = std::getenv("NSB200_TRACE") != nullptr;
-    const auto t0 = std::chrono::steady_clock::now();
-    {
-        std::shared_lock<std::shared_mutex> lk(e->mu);
-        resolve_all(e, Q, [&](uint32_t q) { return starts[q]; }, r);
-    }
-    if (trace)
-        std::fprintf(stderr, "[nsb200] Q=%u resolve %.3f ms (%llu terms)\n", Q,
-                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(),
-                     (unsigned long long)r.q_off[Q]);
-    if (has_found && Q) std::memcpy(has_found, r.has.data(), Q);
-    return ns_search_batch(e->idx, Q, k, r.q_off.data(), r.terms.data(), out_hits, out_nhits, out_found);
+    auto gen = e->snapshot();
+    if (!gen) { set_error("search before a successful reload"); return NS_ERR_STATE; }
+    const Generation& g = *gen;
+    return search_core(e, gen, Q, [&](uint32_t q, std::vector<QueryTerm>& qt) { return query_terms_of(g, starts[q], qt); }, k,
+                       out_hits, out_nhits, out_found, has_found);
 }
 
+// Explicit qterms_w lists (the reference's vector<pair<string, float>> of src/api_engine.cpp:410-421), one per
+// query: t_off[Q+1] indexes terms[] / weights[].  No tokenisation, no filter, no expansion: exactly what the
+// scoring loop (:426-505) receives.
+extern "C" int ns_engine_search_terms_batch(ns_engine* e, uint32_t Q, const uint64_t* t_off, const char* const* terms,
+                                            const float* weights, int k, ns_hit* out_hits, uint32_t* out_nhits,
+                                            uint64_t* out_found, uint8_t* has_found) {
+    if (!e || !t_off || (Q && t_off[Q] && (!terms || !weights))) { set_error("ns_engine_search_terms_batch: null argument"); return NS_ERR_INVALID; }
+    if (e->idx.empty()) { set_error("engine was created without a CUDA device; there is no CPU search path"); return NS_ERR_STATE; }
+    auto gen = e->snapshot();
+    if (!gen) { set_error("search before a successful reload"); return NS_ERR_STATE; }
+    const Generation& g = *gen;
+    auto terms_of = [&](uint32_t q, std::vector<QueryTerm>& qt) {
+        qt.clear();
+        for (uint64_t i = t_off[q]; i < t_off[q + 1]; i++) {
+            const size_t n = std::strlen(terms[i]);
+            const int64_t gid = g.dict.find(terms[i], n, term_hash(terms[i], n));
+            if (gid >= 0) qt.push_back(QueryTerm{(uint32_t)gid, weights[i]});
+        }
+        return t_off[q + 1] > t_off[q] && !g.seg_names.empty();  // :407, :424
+    };
+    return search_core(e, gen, Q, terms_of, k, out_hits, out_nhits, out_found, has_found);
+}
+
+// SemanticIndex::expand for one query (src/api_engine.cpp:410-417): the kept tokens are expanded with the
+// loaded embeddings.  Terms come back NUL-separated in `buf`, weights in `weights`; returns the count, -1
+// if a buffer is too small, 0 with *enabled = 0 when no embeddings are loaded.
+extern "C" int ns_engine_expand(ns_engine* e, const char* query, char* buf, size_t cap, float* weights, int wcap, int* enabled) {
+    if (enabled) *enabled = 0;
+    if (!e || !query || !buf) return -1;
+    auto gen = e->snapshot();
+    if (!gen || !gen->sem.enabled) return 0;
+    if (enabled) *enabled = 1;
+    std::vector<std::string> base;
+    query_terms(query, base);
+    if (base.empty()) return 0;
+    const auto qw = gen->sem.expand(base);
+    size_t at = 0;
+    int n = 0;
+    for (auto& tw : qw) {
+        if (at + tw.first.size() + 1 > cap || n >= wcap) return -1;
+        std::memcpy(buf + at, tw.first.c_str(), tw.first.size() + 1);
+        at += tw.first.size() + 1;
+        if (weights) weights[n] = tw.second;
+        n++;
+    }
+    return n;
+}
+
+extern "C" int ns_engine_search_one(ns_engine* e, const char* query, int k, ns_hit* out_hits, uint32_t* out_nhits,
+                                    uint64_t* out_found, uint8_t* has_found) {
+    if (!e || !query) { set_error("ns_engine_search_one: null argument"); return NS_ERR_INVALID; }
+    if (e->idx.empty()) { set_error("engine was created without a CUDA device; there is no CPU search path"); return NS_ERR_STATE; }
+    return search_one(e, query, k, out_hits, out_nhits, out_found, has_found, nullptr);
+}
+
+extern "C" int ns_engine_coalescer_start(ns_engine* e, uint32_t max_batch, uint32_t max_wait_us, int dispatchers) {
+    if (!e) return NS_ERR_INVALID;
+    if (e->idx.empty()) { set_error("engine was created without a CUDA device; there is no CPU search path"); return NS_ERR_STATE; }
+    std::lock_guard<std::mutex> lk(e->co_mu);
+    if (e->coalescer) { set_error("coalescer already running"); return NS_ERR_STATE; }
+    e->coalescer.reset(new Coalescer(e, max_batch ? max_batch : 4096, max_wait_us, dispatchers > 0 ? dispatchers : 2));
+    return NS_OK;
+}
+
+extern "C" int ns_engine_coalescer_stop(ns_engine* e) {
+    if (!e) return NS_ERR_INVALID;
+    std::unique_ptr<Coalescer> c;
+    {
+        std::lock_guard<std::mutex> lk(e->co_mu);
+        c = std::move(e->coalescer);
+    }
+    c.reset();  // serves what is queued, then joins
+    return NS_OK;
+}
+
+extern "C" int ns_engine_coalescer_stats(ns_engine* e, uint64_t* batches, uint64_t* queries, uint64_t* max_batch_seen) {
+    if (!e) return NS_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(e->co_mu);
+    if (batches) *batches = e->coalescer ? e->coalescer->n_batches.load() : 0;
+    if (queries) *queries = e->coalescer ? e->coalescer->n_queries.load() : 0;
+    if (max_batch_seen) *max_batch_seen = e->coalescer ? e->coalescer->max_seen.load() : 0;
+    return NS_OK;
+}
+
+// Engine::search (src/api_engine.cpp:369-542) as JSON text, byte-compatible with nlohmann's dump() of the
+// reference's object: keys in lexicographic order, floats via Grisu2 (json_text.hpp).
 extern "C" int ns_engine_search_json(ns_engine* e, const char* query, int k, char* buf, size_t cap, size_t* needed) {
     if (!e || !query) { set_error("ns_engine_search_json: null argument"); return NS_ERR_INVALID; }
+    if (e->idx.empty()) { set_error("engine was created without a CUDA device; there is no CPU search path"); return NS_ERR_STATE; }
     const int K = std::max(1, std::min(k, NS_MAX_K));  // src/api_engine.cpp:377
     std::vector<ns_hit> hits((size_t)K);
     uint32_t nh = 0;
     uint64_t found = 0;
     uint8_t has = 0;
-    const char* qs[1] = {query};
-    int rc = ns_engine_search_batch(e, 1, qs, K, hits.data(), &nh, &found, &has);
+    std::shared_ptr<const Generation> gen;
+    int rc = search_one(e, query, K, hits.data(), &nh, &found, &has, &gen);
     if (rc != NS_OK) return rc;
-    std::shared_lock<std::shared_mutex> lk(e->mu);
-    // nlohmann::json objects dump with keys in lexicographic order
+    const Generation& g = *gen;  // names, uids and metadata of the generation that produced the hits
     std::string out = "{";
+    bool ok = true;
     if (has) out += "\"found\":" + std::to_string(found) + ",";
-    out += "\"k\":" + std::to_string(K) + ",\"query\":\"";
-    json_escape(query, out);
-    out += "\",\"results\":[";
-    for (uint32_t i = 0; i < nh; i++) {
+    out += "\"k\":" + std::to_string(K) + ",\"query\":";
+    ok = ok && jsontext::append_string(out, query, std::strlen(query));
+    out += ",\"results\":[";
+    MetaFields mf;
+    for (uint32_t i = 0; i < nh && ok; i++) {
         const ns_hit& h = hits[i];
         if (i) out += ",";
-        out += "{\"cord_uid\":\"";
-        if (h.seg < e->segs.size() && e->segs[h.seg]) json_escape(e->segs[h.seg]->cord_uid(h.doc), out);
-        out += "\",\"docId\":" + std::to_string(h.doc) + ",\"score\":";
-        json_double((double)h.score, out);
-        out += ",\"segment\":\"";
-        if (h.seg < e->seg_names.size()) json_escape(e->seg_names[h.seg], out);
-        out += "\"}";
+        const std::string uid = (h.seg < g.segs.size() && g.segs[h.seg]) ? g.segs[h.seg]->cord_uid(h.doc) : std::string();
+        const bool decorated = g.meta.enabled() && g.meta.lookup(uid, mf);  // :516-532
+        out += "{";
+        if (decorated && !mf.author.empty()) {
+            out += "\"author\":";
+            ok = ok && jsontext::append_string(out, mf.author);
+            out += ",";
+        }
+        out += "\"cord_uid\":";
+        ok = ok && jsontext::append_string(out, uid);
+        out += ",\"docId\":" + std::to_string(h.doc);
+        if (decorated && !mf.publish_time.empty()) {
+            out += ",\"publish_time\":";
+            ok = ok && jsontext::append_string(out, mf.publish_time);
+        }
+        out += ",\"score\":";
+        jsontext::append_double(out, (double)h.score);  // r["score"] = h.s widens the f32 (:511)
+        out += ",\"segment\":";
+        ok = ok && jsontext::append_string(out, h.seg < g.seg_names.size() ? g.seg_names[h.seg] : std::string());
+        if (decorated) {
+            if (!mf.title.empty()) {
+                out += ",\"title\":";
+                ok = ok && jsontext::append_string(out, mf.title);
+            }
+            std::string url = mf.url;
+            const size_t semi = url.find(';');
+            if (semi != std::string::npos) url = url.substr(0, semi);  // :524-526
+            if (!url.empty()) {
+                out += ",\"url\":";
+                ok = ok && jsontext::append_string(out, url);
+            }
+        }
+        out += "}";
     }
-    out += "],\"segments\":" + std::to_string(e->seg_names.size()) + "}";
+    out += "],\"segments\":" + std::to_string(g.seg_names.size()) + "}";
+    if (!ok) {
+        // nlohmann::json::dump throws type_error.316 on invalid UTF-8 and the reference's HTTP handler answers 500
+        set_error("query or result field is not valid UTF-8 (the reference's json::dump throws type_error.316)");
+        return NS_ERR_INVALID;
+    }
     if (needed) *needed = out.size();
     if (buf && cap) {
         size_t n = std::min(cap - 1, out.size());

@@ -104,10 +104,10 @@ bool parse_lexicon(const std::vector<uint8_t>& bytes, uint32_t barrel, uint64_t 
     return true;
 }
 
-bool slurp_into(const std::string& path, std::vector<uint64_t>& dst, uint64_t at, uint64_t nbytes) {
+bool slurp_into(const std::string& path, uint8_t* dst, uint64_t at, uint64_t nbytes) {
     FILE* f = std::fopen(path.c_str(), "rb");
     if (!f) return false;
-    size_t got = nbytes ? std::fread((uint8_t*)dst.data() + at * 8, 1, nbytes, f) : 0;
+    size_t got = nbytes ? std::fread(dst + at * 8, 1, nbytes, f) : 0;
     std::fclose(f);
     return got == nbytes;
 }
@@ -124,7 +124,7 @@ uint64_t file_size(const std::string& path, bool& ok) {
 
 }  // namespace
 
-bool load_segment(const std::string& segdir, HostSegment& s, int nthreads) {
+bool load_segment(const std::string& segdir, HostSegment& s, int nthreads, PostingSink* sink) {
     s = HostSegment{};
     s.dir = segdir;
     std::vector<uint8_t> bytes;
@@ -181,15 +181,27 @@ bool load_segment(const std::string& segdir, HostSegment& s, int nthreads) {
             if (inv_bytes[b] % 8 != 0) { set_error("inverted barrel size is not a multiple of 8 in " + segdir); return false; }
             base[b + 1] = base[b] + inv_bytes[b] / 8;
         }
-        s.postings.resize(base[B]);
+        uint8_t* dst = nullptr;
+        if (sink) {
+            dst = sink->begin(base[B]);
+            if (!dst) return false;  // the sink set the error text
+        } else {
+            s.postings.resize(base[B]);
+            dst = (uint8_t*)s.postings.data();
+        }
+        // largest barrels first: barrel 0 holds the most frequent terms (about half of all postings)
+        std::vector<uint32_t> by_size(B);
+        for (uint32_t b = 0; b < B; b++) by_size[b] = b;
+        std::stable_sort(by_size.begin(), by_size.end(), [&](uint32_t x, uint32_t y) { return inv_bytes[x] > inv_bytes[y]; });
         std::atomic<uint32_t> next{0};
         std::atomic<bool> fail{false};
         auto work = [&]() {
             for (;;) {
-                uint32_t b = next.fetch_add(1);
-                if (b >= B) break;
-                if (!slurp_into(segdir + "/inverted_b" + barrel_suffix(b) + ".bin", s.postings, base[b], inv_bytes[b]))
-                    fail = true;
+                uint32_t i = next.fetch_add(1);
+                if (i >= B) break;
+                const uint32_t b = by_size[i];
+                if (!slurp_into(segdir + "/inverted_b" + barrel_suffix(b) + ".bin", dst, base[b], inv_bytes[b])) fail = true;
+                else if (sink) sink->filled(base[b], inv_bytes[b] / 8);
             }
         };
         int nt = std::max(1, std::min(nthreads, (int)B));
@@ -212,8 +224,16 @@ bool load_segment(const std::string& segdir, HostSegment& s, int nthreads) {
         uint64_t nb = file_size(segdir + "/inverted.bin", ok);
         if (!ok) { set_error("cannot open " + segdir + "/inverted.bin"); return false; }
         if (nb % 8 != 0) { set_error("inverted.bin size is not a multiple of 8 in " + segdir); return false; }
-        s.postings.resize(nb / 8);
-        if (!slurp_into(segdir + "/inverted.bin", s.postings, 0, nb)) { set_error("short read of inverted.bin in " + segdir); return false; }
+        uint8_t* dst = nullptr;
+        if (sink) {
+            dst = sink->begin(nb / 8);
+            if (!dst) return false;
+        } else {
+            s.postings.resize(nb / 8);
+            dst = (uint8_t*)s.postings.data();
+        }
+        if (!slurp_into(segdir + "/inverted.bin", dst, 0, nb)) { set_error("short read of inverted.bin in " + segdir); return false; }
+        if (sink) sink->filled(0, nb / 8);
         if (!parse_lexicon(bytes, 0, 0, nb, s.rows, terms, lp)) return false;
     }
 
@@ -222,8 +242,55 @@ bool load_segment(const std::string& segdir, HostSegment& s, int nthreads) {
         s.rows[i].idf = bm25_idf(s.N, s.rows[i].df);
         s.lex.emplace(std::move(terms[i]), i);  // emplace: first entry for a term wins
     }
-    s.table.build(s.lex);
     return true;
+}
+
+void TermDict::build(const std::vector<std::unique_ptr<HostSegment>>& segs) {
+    owned.clear();
+    for (size_t i = 0; i < segs.size(); i++)
+        if (segs[i]) owned.push_back((uint32_t)i);
+    size_t upper = 0;
+    for (uint32_t i : owned) upper += segs[i]->lex.size();
+    size_t cap = 16;
+    while (cap < upper * 2 + 1) cap <<= 1;  // sized for the worst case (disjoint vocabularies): no rehash
+    slots.assign(cap, Slot{});
+    mask = cap - 1;
+    keys.clear();
+    nterms = 0;
+    // pass 1: intern every term, remember per segment the gid of each row
+    std::vector<std::vector<uint32_t>> gid_of(owned.size());
+    for (size_t j = 0; j < owned.size(); j++) {
+        const HostSegment& sg = *segs[owned[j]];
+        gid_of[j].assign(sg.rows.size(), kAbsent);
+        for (auto& kv : sg.lex) {
+            const std::string& term = kv.first;
+            const uint64_t h = term_hash(term.data(), term.size());
+            size_t i = (size_t)(h & mask);
+            for (;; i = (i + 1) & mask) {
+                Slot& sl = slots[i];
+                if (sl.gid == kAbsent) {
+                    sl.h = h;
+                    sl.key_off = (uint32_t)keys.size();
+                    sl.key_len = (uint32_t)term.size();
+                    sl.gid = nterms++;
+                    keys.insert(keys.end(), term.begin(), term.end());
+                    break;
+                }
+                if (sl.h == h && sl.key_len == term.size() && std::memcmp(keys.data() + sl.key_off, term.data(), term.size()) == 0) break;
+            }
+            gid_of[j][kv.second] = slots[i].gid;
+        }
+    }
+    // pass 2: the dense (term, segment) table
+    table.assign((size_t)nterms * owned.size(), Entry{kAbsent, 0.0f});
+    for (size_t j = 0; j < owned.size(); j++) {
+        const HostSegment& sg = *segs[owned[j]];
+        for (size_t r = 0; r < sg.rows.size(); r++) {
+            const uint32_t g = gid_of[j][r];
+            if (g == kAbsent || sg.rows[r].df == 0) continue;  // shadowed duplicate row, or df == 0
+            table[(size_t)g * owned.size() + j] = Entry{(uint32_t)r, sg.rows[r].idf};
+        }
+    }
 }
 
 }  // namespace nsb

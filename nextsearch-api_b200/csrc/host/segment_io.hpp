@@ -5,6 +5,7 @@
 #pragma once
 #include <cstdint>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -27,41 +28,15 @@ inline uint64_t term_hash(const char* p, size_t n) {
     return h;
 }
 
-// Flat open-addressing view of HostSegment::lex for the query front end (one cache line per probe,
-// hash computed by the caller).  Keys point into the map's own nodes, which never move.
-struct TermTable {
-    struct Slot {
-        uint64_t h = 0;
-        const std::string* key = nullptr;  // nullptr = empty
-        uint32_t row = 0;
-        uint32_t pad = 0;
-    };
-    std::vector<Slot> slots;
-    uint64_t mask = 0;
-
-    void build(const std::unordered_map<std::string, uint32_t>& lex) {
-        size_t cap = 16;
-        while (cap < lex.size() * 2 + 1) cap <<= 1;
-        slots.assign(cap, Slot{});
-        mask = cap - 1;
-        for (auto& kv : lex) {
-            const uint64_t h = term_hash(kv.first.data(), kv.first.size());
-            size_t i = (size_t)(h & mask);
-            while (slots[i].key) i = (i + 1) & mask;
-            slots[i].h = h;
-            slots[i].key = &kv.first;
-            slots[i].row = kv.second;
-        }
-    }
-    // row of the term, or -1
-    int64_t find(const char* p, size_t n, uint64_t h) const {
-        if (slots.empty()) return -1;
-        for (size_t i = (size_t)(h & mask);; i = (i + 1) & mask) {
-            const Slot& s = slots[i];
-            if (!s.key) return -1;
-            if (s.h == h && s.key->size() == n && std::memcmp(s.key->data(), p, n) == 0) return (int64_t)s.row;
-        }
-    }
+// Where load_segment puts the posting bytes.  The default keeps them in HostSegment::postings; the engine
+// supplies a sink backed by pinned memory whose filled() starts the host->device copy of every finished
+// barrel while the other barrels are still being read (ns_upload_*).
+struct PostingSink {
+    virtual ~PostingSink() = default;
+    // called once: room for P postings (8 bytes each) or nullptr on failure
+    virtual uint8_t* begin(uint64_t P) = 0;
+    // postings [first, first + count) are in place; may be called from several reader threads
+    virtual void filled(uint64_t first, uint64_t count) = 0;
 };
 
 struct HostSegment {
@@ -73,7 +48,6 @@ struct HostSegment {
     std::vector<uint64_t> uid_off;   // [n+1]
     std::vector<LexRow> rows;
     std::unordered_map<std::string, uint32_t> lex;  // term -> row (first occurrence wins, like emplace)
-    TermTable table;                                // the same mapping, flat (built by load_segment)
     std::vector<uint64_t> postings;  // interleaved {u32 docId, u32 tf} = file bytes
     bool use_barrels = false;
     uint32_t barrel_count = 0, terms_per_barrel = 0;
@@ -89,8 +63,45 @@ struct HostSegment {
 float bm25_idf(uint32_t N, uint32_t df);
 
 // src/api_segment.cpp:105-136.  Returns false (error text set) if a file is missing or truncated.
-// nthreads > 1 reads barrels in parallel.
-bool load_segment(const std::string& segdir, HostSegment& s, int nthreads = 1);
+// nthreads > 1 reads barrels in parallel.  sink != nullptr receives the postings instead of s.postings.
+bool load_segment(const std::string& segdir, HostSegment& s, int nthreads = 1, PostingSink* sink = nullptr);
+
+// One dictionary over the lexicons of all segments an engine owns: a query token is hashed and probed ONCE,
+// and its (row, idf) in every owned segment sits in one contiguous run — the front end's cost per token no
+// longer grows with the number of segments (the reference probes one unordered_map per segment,
+// src/api_engine.cpp:454).  Open addressing, 64-bit FNV-1a computed by the caller, keys compared in full.
+struct TermDict {
+    static constexpr uint32_t kAbsent = 0xFFFFFFFFu;
+    struct Entry {
+        uint32_t row;  // kAbsent: the term is not in that segment, or its df is 0 (src/api_engine.cpp:455,458)
+        float idf;     // bm25_idf(N, df) of that segment
+    };
+    struct Slot {
+        uint64_t h = 0;
+        uint32_t key_off = 0, key_len = 0;
+        uint32_t gid = kAbsent;  // kAbsent = empty slot
+        uint32_t pad = 0;
+    };
+    std::vector<uint32_t> owned;   // global segment index of column j, ascending
+    std::vector<Slot> slots;
+    uint64_t mask = 0;
+    std::vector<char> keys;
+    std::vector<Entry> table;      // [gid * owned.size() + j]
+    uint32_t nterms = 0;
+
+    // segs[i] may be null (not owned)
+    void build(const std::vector<std::unique_ptr<HostSegment>>& segs);
+    // global term id or -1
+    int64_t find(const char* p, size_t n, uint64_t h) const {
+        if (slots.empty()) return -1;
+        for (size_t i = (size_t)(h & mask);; i = (i + 1) & mask) {
+            const Slot& s = slots[i];
+            if (s.gid == kAbsent) return -1;
+            if (s.h == h && s.key_len == n && std::memcmp(keys.data() + s.key_off, p, n) == 0) return (int64_t)s.gid;
+        }
+    }
+    const Entry* row_of(uint32_t gid) const { return table.data() + (size_t)gid * owned.size(); }
+};
 
 // src/api_segment.cpp:14-42
 std::vector<std::string> load_manifest(const std::string& manifest_path);

@@ -1,6 +1,6 @@
 // Persistent host worker pool for the query front end: spawning std::threads per batch costs
 // ~0.5 ms, a good part of a 2 ms batch.  run(n, fn) executes fn(0..n-1), the caller taking part,
-// and returns when all are done.  One run at a time per pool (callers serialise on run_mu).
+// and returns when all are done.
 #pragma once
 #include <atomic>
 #include <condition_variable>
@@ -32,7 +32,13 @@ class WorkPool {
             for (int i = 0; i < n; i++) fn(i);
             return;
         }
-        std::lock_guard<std::mutex> one(run_mu_);
+        // One parallel run at a time.  A caller that finds the pool busy (several threads are inside the
+        // engine) does its work inline: the concurrency then comes from the callers themselves.
+        std::unique_lock<std::mutex> one(run_mu_, std::try_to_lock);
+        if (!one.owns_lock()) {
+            for (int i = 0; i < n; i++) fn(i);
+            return;
+        }
         {
             std::lock_guard<std::mutex> lk(mu_);
             fn_ = &fn;

@@ -265,13 +265,22 @@ class Engine:
     rank/world select this engine's segment shard (segment i -> rank i % world).
     """
 
-    def __init__(self, index_dir: str, device: Optional[int] = 0, rank: int = 0, world: int = 1):
+    def __init__(self, index_dir: str, device: Optional[int] = 0, rank: int = 0, world: int = 1,
+                 devices: Optional[Sequence[int]] = None):
+        """devices=[d0, d1, ...] builds ONE engine spanning several GPUs (ns_engine_create_multi): segment j of the
+        engine's share lives on devices[j % len(devices)], results are merged on devices[0]."""
         self._lib = _lib.load()
         h = C.c_void_p()
-        check(self._lib.ns_engine_create(str(index_dir).encode(), -1 if device is None else int(device), C.byref(h)))
+        if devices is not None:
+            arr = (C.c_int * max(1, len(devices)))(*[int(d) for d in devices])
+            check(self._lib.ns_engine_create_multi(str(index_dir).encode(), len(devices), arr, C.byref(h)))
+            device = devices[0] if devices else None
+        else:
+            check(self._lib.ns_engine_create(str(index_dir).encode(), -1 if device is None else int(device), C.byref(h)))
         self._h = h
         self.index_dir = str(index_dir)
         self.device = device
+        self.devices = list(devices) if devices is not None else ([] if device is None else [device])
         self.rank, self.world = rank, world
         check(self._lib.ns_engine_set_shard(self._h, rank, world))
 
@@ -388,6 +397,85 @@ class Engine:
             check(self._lib.ns_engine_search_batch_packed(self._h, Q, z, len(z), int(k), _ptr(hits), _ptr(nhits),
                                                           _ptr(found), _ptr(has)))
         return BatchResult(hits, nhits, found, has[:Q].astype(bool), K)
+
+    def search_terms_batch(self, term_lists: Sequence[Sequence[Tuple[str, float]]], k: int = 10) -> BatchResult:
+        """Explicit (term, qweight) lists — the reference's qterms_w — one per query (ns_engine_search_terms_batch)."""
+        Q = len(term_lists)
+        K = clamp_k(k)
+        t_off = np.zeros(Q + 1, dtype=np.uint64)
+        flat_t, flat_w = [], []
+        for q, lst in enumerate(term_lists):
+            for t, w in lst:
+                flat_t.append(t)
+                flat_w.append(w)
+            t_off[q + 1] = len(flat_t)
+        terms = _cstr_array(flat_t)
+        weights = np.ascontiguousarray(flat_w if flat_w else [0.0], dtype=np.float32)
+        hits = np.zeros((Q, K), dtype=HIT_DTYPE)
+        nhits = np.zeros(Q, dtype=np.uint32)
+        found = np.zeros(Q, dtype=np.uint64)
+        has = np.zeros(max(1, Q), dtype=np.uint8)
+        check(self._lib.ns_engine_search_terms_batch(self._h, Q, _ptr(t_off), terms, _ptr(weights), int(k), _ptr(hits),
+                                                     _ptr(nhits), _ptr(found), _ptr(has)))
+        return BatchResult(hits, nhits, found, has[:Q].astype(bool), K)
+
+    def expand(self, query: str) -> Optional[List[Tuple[str, float]]]:
+        """SemanticIndex::expand of the query's kept tokens; None when no embeddings are loaded."""
+        cap = 1 << 16
+        buf = C.create_string_buffer(cap)
+        w = np.zeros(64, dtype=np.float32)
+        en = C.c_int()
+        n = self._lib.ns_engine_expand(self._h, query.encode("utf-8"), buf, cap, _ptr(w), 64, C.byref(en))
+        if not en.value:
+            return None
+        if n < 0:
+            raise RuntimeError("ns_engine_expand: buffer too small")
+        raw, out, at = buf.raw, [], 0
+        for i in range(n):
+            end = raw.index(b"\0", at)
+            out.append((raw[at:end].decode("utf-8", "replace"), float(w[i])))
+            at = end + 1
+        return out
+
+    def search_one(self, query: str, k: int = 10):
+        """One query, blocking; coalesced with other threads' queries when the coalescer runs.
+        Returns (hits[:n], found or None)."""
+        K = clamp_k(k)
+        hits = np.zeros(K, dtype=HIT_DTYPE)
+        n, f, h = C.c_uint32(), C.c_uint64(), C.c_uint8()
+        check(self._lib.ns_engine_search_one(self._h, query.encode("utf-8"), int(k), _ptr(hits), C.byref(n), C.byref(f),
+                                             C.byref(h)))
+        return hits[: n.value], (f.value if h.value else None)
+
+    def coalescer_start(self, max_batch: int = 4096, max_wait_us: int = 200, dispatchers: int = 2) -> None:
+        check(self._lib.ns_engine_coalescer_start(self._h, int(max_batch), int(max_wait_us), int(dispatchers)))
+
+    def coalescer_stop(self) -> None:
+        check(self._lib.ns_engine_coalescer_stop(self._h))
+
+    def coalescer_stats(self) -> dict:
+        b, q, m = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        check(self._lib.ns_engine_coalescer_stats(self._h, C.byref(b), C.byref(q), C.byref(m)))
+        return {"batches": b.value, "queries": q.value, "max_batch": m.value}
+
+    def reload_stats(self) -> dict:
+        t, r, d = C.c_double(), C.c_double(), C.c_double()
+        pb, db = C.c_uint64(), C.c_uint64()
+        check(self._lib.ns_engine_reload_stats(self._h, C.byref(t), C.byref(r), C.byref(d), C.byref(pb), C.byref(db)))
+        return {"total_s": t.value, "read_upload_s": r.value, "dict_s": d.value, "posting_bytes": pb.value,
+                "device_bytes": db.value}
+
+    def search_json_text(self, query: str, k: int = 10) -> str:
+        """The raw text ns_engine_search_json returns (byte-compatible with the reference's j.dump())."""
+        q = query.encode("utf-8") if isinstance(query, str) else query
+        cap = 1 << 16
+        while True:
+            buf = C.create_string_buffer(cap)
+            need = C.c_size_t()
+            check(self._lib.ns_engine_search_json(self._h, q, int(k), buf, cap, C.byref(need)))
+            if need.value < cap:
+                return buf.raw[: need.value].decode("utf-8")
+            cap = need.value + 1
 
     def close(self) -> None:
         if self._h:

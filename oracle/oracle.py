@@ -52,6 +52,9 @@ def load() -> C.CDLL:
     lib.orc_query_terms.argtypes = [C.c_char_p, C.POINTER(C.c_char_p), C.c_int]
     lib.orc_search.restype = C.c_int
     lib.orc_search.argtypes = [P, C.c_char_p, C.c_int, P, P, P, C.POINTER(C.c_uint64), C.POINTER(C.c_int)]
+    lib.orc_search_weighted.restype = C.c_int
+    lib.orc_search_weighted.argtypes = [P, C.c_int, C.POINTER(C.c_char_p), P, C.c_int, P, P, P, C.POINTER(C.c_uint64),
+                                        C.POINTER(C.c_int)]
     lib.orc_score_doc.argtypes = [P, C.c_char_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_int)]
     lib.orc_search_many.restype = C.c_double
     lib.orc_search_many.argtypes = [P, C.POINTER(C.c_char_p), C.c_int, C.c_int, C.c_int, P, P, P, P, P, P]
@@ -105,6 +108,24 @@ class OracleIndex:
                for i in range(n)]
         return {"query": query, "k": K, "segments": self.num_segments, "found": found.value if has.value else None,
                 "results": res}
+
+    def search_weighted(self, qterms, k: int = 10) -> dict:
+        """The scoring loop over an explicit [(term, weight)] list — the reference's qterms_w."""
+        K = max(1, min(int(k), 100))
+        n = len(qterms)
+        arr = (C.c_char_p * max(1, n))(*[t.encode("utf-8") for t, _ in qterms])
+        w = np.ascontiguousarray([x for _, x in qterms] if n else [0.0], dtype=np.float32)
+        s = np.zeros(100, np.float32)
+        g = np.zeros(100, np.uint32)
+        d = np.zeros(100, np.uint32)
+        found, has = C.c_uint64(), C.c_int()
+        nh = self.lib.orc_search_weighted(self.h, n, arr, _p(w), int(k), _p(s), _p(g), _p(d), C.byref(found), C.byref(has))
+        if nh < 0:
+            raise ValueError("too many terms")
+        res = [{"score": float(s[i]), "score_bits": int(s[i:i + 1].view(np.uint32)[0]), "seg": int(g[i]),
+                "segment": self.segment_name(int(g[i])), "docId": int(d[i]), "cord_uid": self.cord_uid(int(g[i]), int(d[i]))}
+               for i in range(nh)]
+        return {"k": K, "segments": self.num_segments, "found": found.value if has.value else None, "results": res}
 
     def score_doc(self, query: str, seg: int, doc: int):
         sc, m = C.c_float(), C.c_int()

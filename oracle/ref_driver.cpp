@@ -30,6 +30,7 @@
 #include "api_engine.hpp"
 #include "api_segment.hpp"
 #include "segment_writer.hpp"
+#include "textutil.hpp"
 
 using cord19::json;
 
@@ -125,6 +126,29 @@ static int mode_search(int argc, char** argv) {
                 search_s += dt;
                 lat.push_back(dt);
                 if (os.is_open()) {
+                    // the exact text the reference's HTTP layer would send (res.set_content(j.dump(2)...) aside,
+                    // dump() is the canonical form): kept verbatim for byte-level comparison
+                    const std::string text = j.dump();
+                    // qterms_w as Engine::search computed it (src/api_engine.cpp:410-417): expand() is const and
+                    // deterministic, so calling it again with the same base terms yields the same list
+                    if (engine.sem.enabled) {
+                        std::vector<std::string> base;
+                        for (auto& t : tokenize(q)) {
+                            if (t.size() < 2) continue;
+                            if (is_stopword(t)) continue;
+                            base.push_back(t);
+                        }
+                        json qt = json::array();
+                        if (!base.empty()) {
+                            for (auto& tw : engine.sem.expand(base, 3, 5, 0.55f, 0.6f, 40)) {
+                                uint32_t wb;
+                                std::memcpy(&wb, &tw.second, 4);
+                                qt.push_back(json::array({tw.first, wb}));
+                            }
+                        }
+                        j["_qterms"] = qt;
+                    }
+                    j["_text"] = text;
                     // score as the exact f32 bit pattern: r["score"] holds the float widened to double
                     for (auto& r : j["results"]) {
                         float f = (float)r["score"].get<double>();

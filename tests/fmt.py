@@ -140,3 +140,92 @@ HANDMADE_QUERIES = [
 def tie_docs(n: int, base: int) -> List[Doc]:
     """n identical docs: term 'aa' tf=1, doc_len 10 (SURVEY.md Appendix B probe)."""
     return [(f"tie{base + i}", 10, [("aa", 1)]) for i in range(n)]
+
+
+# ---- corpus with embeddings and metadata.csv: semantic expansion (weights != 1, > 5 terms) and result
+# ---- decoration, both as the reference itself produces them (tests/golden/semantic.json) ----
+
+_SEM_CLUSTERS = [
+    ["virus", "viral", "viruses", "corona", "covid", "sars"],
+    ["vaccine", "vaccines", "immunity", "antibody", "antibodies"],
+    ["mask", "masks", "respirator", "ppe"],
+    ["lung", "lungs", "pneumonia", "fever", "cough"],
+    ["bat", "bats", "pangolin", "spillover"],
+    ["spike", "protein", "rna", "genome", "gene"],
+]
+SEM_VOCAB = [w for c in _SEM_CLUSTERS for w in c]
+SEM_DIM = 12
+
+
+def _lcg(seed: int):
+    x = seed & 0xFFFFFFFF
+    while True:
+        x = (x * 1664525 + 1013904223) & 0xFFFFFFFF
+        yield x
+
+
+def semantic_docs(seg: int) -> List[Doc]:
+    """Segment `seg` (0 or 1): 24 docs over SEM_VOCAB, every doc with its own length and tf pattern
+    (no two docs share a (tf, dl) pair for a term, so scores do not tie)."""
+    rng = _lcg(1000 + seg)
+    docs = []
+    for d in range(24):
+        nterms = 2 + next(rng) % 5
+        picked, tfs = [], []
+        for _ in range(nterms):
+            w = SEM_VOCAB[next(rng) % len(SEM_VOCAB)]
+            if w in picked:
+                continue
+            picked.append(w)
+            tfs.append((w, 1 + next(rng) % 4))
+        dl = 20 + 7 * d + seg * 3 + sum(tf for _, tf in tfs)
+        docs.append((f"uid{seg}_{d:02d}", dl, tfs))
+    return docs
+
+
+def semantic_embeddings_text() -> str:
+    """embeddings.vec: header, clustered vectors (cosine ~0.9 inside a cluster, ~0 across), plus lines the loader
+    must skip: a word outside the lexicon, a short vector, a vector of another dimension, a repeated word."""
+    rng = _lcg(77)
+    lines = [f"{len(SEM_VOCAB) + 4} {SEM_DIM}"]
+    for ci, cluster in enumerate(_SEM_CLUSTERS):
+        for wi, w in enumerate(cluster):
+            v = []
+            for j in range(SEM_DIM):
+                base = 1.0 if j == 2 * ci or j == 2 * ci + 1 else 0.0
+                noise = ((next(rng) % 2001) - 1000) / 1000.0 * (0.18 + 0.05 * wi)
+                v.append(base + noise)
+            lines.append(w + " " + " ".join(f"{x:.4f}" for x in v))
+    lines.append("notindexed " + " ".join("0.5" for _ in range(SEM_DIM)))      # filtered: not in any lexicon
+    lines.append("rna 0.1 0.2 0.3")                                            # < 10 values: skipped
+    lines.append("gene " + " ".join("0.25" for _ in range(SEM_DIM + 3)))      # other dimension: skipped
+    lines.append("virus " + " ".join("0.3" for _ in range(SEM_DIM)))          # repeated word: first row stays the word's row
+    lines.append("")
+    return "\n".join(lines) + "\n"
+
+
+SEM_QUERIES = [
+    "virus", "covid vaccine", "masks", "bat virus spike", "the lung", "unknownword", "virus virus",
+    "fever cough rna", "antibody", "Spike PROTEIN, of the genome!", "pangolin spillover bats", "ppe respirator mask gene",
+]
+
+
+def metadata_csv_text() -> str:
+    """metadata.csv for the semantic corpus: quoted commas, several authors, a romanised name in parentheses,
+    empty fields, a repeated uid (first row wins), a short row, a row ending in CR LF, url lists with ';'."""
+    hdr = "cord_uid,sha,source_x,title,doi,publish_time,authors,journal,url"
+    rows = [
+        'uid0_00,s0,PMC,"Coronaviruses, bats and spillover",10.1/a,2020-01-15,"Zhou, Peng; Yang, Xing-Lou; Wang, Xian-Guang",Nature,https://a.example/1; https://b.example/1',
+        'uid0_01,s1,PMC,Plain title,10.1/b,2019,"Smith John",J Virol,https://a.example/2',
+        'uid0_02,s2,WHO,"Quoted ""title"" here",,2020-03,"(Li Wei) 李伟; Chen, Q",,',
+        'uid0_03,s3,PMC,,10.1/d,,"  ,  ",Lancet,https://a.example/4',
+        'uid0_04,s4,PMC,Title four,10.1/e,2021-05-06,"Garcia-Lopez, Maria,",BMJ,;https://second.example',
+        'uid0_05,s5',
+        'uid0_06,s6,PMC,Tab\tin title,10.1/f,2020,"van der Waals, J; Other, A",Cell,https://a.example/6\r',
+        'uid0_00,dup,PMC,SHOULD NOT APPEAR,x,1999,"Nobody, N",None,https://dup.example',
+        'uid1_00,t0,PMC,Second segment doc,10.2/a,2020-12-31,"Müller, Jürgen",Science,https://c.example/0',
+        'uid1_03,t3,PMC,"Only, title",,,,,',
+        ',nouid,PMC,row without uid,,,,,',
+        'uid1_07,t7,PMC,Single name,10.2/h,2018-07,"Aristotle",Mind,https://c.example/7;',
+    ]
+    return hdr + "\n" + "\n".join(rows) + "\n"

@@ -14,6 +14,10 @@ Outputs
                        + Engine::search results for generated and edge-case queries at several k
   handmade.json        the same for the 12-doc hand-made corpus of tests/fmt.py (barrels and legacy)
   ties.json            2 segments x 1000 identical docs: found, scores, which segment wins
+  semantic.json        2 x 24-doc corpus WITH embeddings.vec and metadata.csv (tests/fmt.py): for every query the
+                       reference's expanded (term, weight bits) list (SemanticIndex::expand), its results, and the
+                       exact text of its JSON (j.dump()) including title / url / publish_time / author; the same
+                       queries on the same index without the embeddings file (decoration only)
 """
 from __future__ import annotations
 
@@ -39,14 +43,19 @@ def sha_dir(d):
     return {f: hashlib.sha256(open(os.path.join(d, f), "rb").read()).hexdigest() for f in sorted(os.listdir(d))}
 
 
-def compact(results):
-    """Engine::search JSON -> compact rows."""
+def compact(results, text=False):
+    """Engine::search JSON -> compact rows (text=True keeps the reference's own j.dump() and qterms_w)."""
     out = []
     for r in results:
-        out.append({
+        row = {
             "query": r["query"], "k": r["k"], "segments": r["segments"], "found": r.get("found"),
             "hits": [[h["segment"], h["docId"], h["score_bits"], h["cord_uid"]] for h in r["results"]],
-        })
+        }
+        if text:
+            row["text"] = r["_text"]
+            if "_qterms" in r:
+                row["qterms"] = r["_qterms"]
+        out.append(row)
     return out
 
 
@@ -93,7 +102,7 @@ def main():
         hand = {"segment_sha256": sha_dir(seg), "search": {}}
         for k in (10, 2):
             _, res = orc.ref_search(hand_idx, fmt.HANDMADE_QUERIES, k)
-            hand["search"][str(k)] = compact(res)
+            hand["search"][str(k)] = compact(res, text=(k == 10))
         # legacy layout: the reference has no writer for multi-doc legacy segments (only
         # src/AddDocument.cpp, one doc); write it with tests/fmt.py and let the REFERENCE read it
         leg_idx = os.path.join(td, "leg_hand")
@@ -119,6 +128,36 @@ def main():
             _, res = orc.ref_search(tie_idx, ["aa", "aa aa"], k)
             ties["search"][str(k)] = compact(res)
         json.dump(ties, open(os.path.join(HERE, "ties.json"), "w"), indent=0)
+        # ---- semantic expansion + metadata decoration ----
+        sem_idx = os.path.join(td, "ref_sem")
+        sem_hash = {}
+        for s in range(2):
+            name = nsb200.seg_name(s + 1)
+            dump = os.path.join(td, f"sem{s}.bin")
+            fmt.write_dump(dump, fmt.semantic_docs(s))
+            seg = os.path.join(sem_idx, "segments", name)
+            orc.ref_write_segment(dump, seg)
+            sem_hash[name] = sha_dir(seg)
+        orc.ref_manifest(sem_idx, [nsb200.seg_name(1), nsb200.seg_name(2)])
+        with open(os.path.join(sem_idx, "metadata.csv"), "w", newline="") as f:
+            f.write(fmt.metadata_csv_text())
+        sem = {"segment_sha256": sem_hash, "plain": {}, "expanded": {}}
+        for k in (10, 3):
+            _, res = orc.ref_search(sem_idx, fmt.SEM_QUERIES, k)      # no embeddings file yet: decoration only
+            sem["plain"][str(k)] = compact(res, text=True)
+        with open(os.path.join(sem_idx, "embeddings.vec"), "w", newline="") as f:
+            f.write(fmt.semantic_embeddings_text())
+        for k in (10, 100):
+            _, res = orc.ref_search(sem_idx, fmt.SEM_QUERIES, k)
+            rows = compact(res, text=True)
+            assert all("qterms" in r for r in rows), "embeddings were not loaded by the reference"
+            sem["expanded"][str(k)] = rows
+        for mode in ("plain", "expanded"):                            # byte-level text parity needs tie-free lists
+            for rows in sem[mode].values():
+                for r in rows:
+                    bits = [h[2] for h in r["hits"]]
+                    assert len(set(bits)) == len(bits), ("score tie in the semantic fixture", r["query"])
+        json.dump(sem, open(os.path.join(HERE, "semantic.json"), "w"), indent=0)
         print("golden fixtures written to", HERE)
     finally:
         shutil.rmtree(td, ignore_errors=True)

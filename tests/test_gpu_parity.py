@@ -315,19 +315,26 @@ def test_foreign_idf_mixes_resident_and_per_batch_scores(small_case, small_engin
     mixed["idf"][::3] = np.nextafter(mixed["idf"][::3], np.float32(10.0))   # 1 ulp off: not resident
     mixed["idf"][1::7] *= np.float32(0.75)
     mixed["weight"][::5] = 0.5
+    # the engine keeps only the resident scores by default (NS_SEG_DROP_RAW); foreign idfs need the raw postings
+    monkeypatch.setenv("NSB200_KEEP_RAW", "1")
+    both = nsb200.Engine(small_case.path, device=0)
+    assert both.reload()
     monkeypatch.setenv("NSB200_NO_RESIDENT", "1")
     monkeypatch.setenv("NSB200_IMPACT", "0")
     plain = nsb200.Engine(small_case.path, device=0)
     assert plain.reload()
+    with pytest.raises(nsb200._lib.NsError):  # default engine: refused loudly, never scored with the wrong idf
+        small_engine.index.search_batch(q_off, mixed, 10)
     for k in (10, 100):
         h0, n0, f0 = plain.index.search_batch(q_off, mixed, k)
-        h1, n1, f1 = small_engine.index.search_batch(q_off, mixed, k)
+        h1, n1, f1 = both.index.search_batch(q_off, mixed, k)
         assert np.array_equal(n0, n1) and np.array_equal(f0, f1)
         for q in range(len(qs)):
             n = int(n0[q])
             assert np.array_equal(h0["score"][q, :n].view(np.uint32), h1["score"][q, :n].view(np.uint32)), qs[q]
             assert np.array_equal(h0["doc"][q, :n], h1["doc"][q, :n]) and np.array_equal(h0["seg"][q, :n], h1["seg"][q, :n])
     plain.close()
+    both.close()
 
 
 def test_sharded_blobs_merge_on_device(workdir):
