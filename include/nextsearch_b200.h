@@ -223,7 +223,7 @@ int ns_batch_launch_exchange(ns_batch* b, ns_exchange* x, uint64_t step, void* s
 int ns_exchange_merge(ns_exchange* x, uint64_t step, uint32_t Q, int k, int spin, void* stream);
 int ns_exchange_result_device(ns_exchange* x, uint64_t step, void** d_blob);
 /* D2H of the merged result of `step` (waits for it).  NS_ERR_STATE if a rank's blob did not arrive within
- * NSB200_EXCHANGE_TIMEOUT_MS (default 2000): the wait is bounded, a missing peer cannot hang the GPU. */
+ * NSB200_EXCHANGE_TIMEOUT_MS (default 10000): the wait is bounded, a missing peer cannot hang the GPU. */
 int ns_exchange_fetch(ns_exchange* x, uint64_t step, uint32_t Q, int k, ns_hit* out_hits, uint32_t* out_nhits,
                       uint64_t* out_found);
 
@@ -316,6 +316,10 @@ int ns_engine_search_one(ns_engine* e, const char* query, int k, ns_hit* out_hit
 int ns_engine_coalescer_start(ns_engine* e, uint32_t max_batch, uint32_t max_wait_us, int dispatchers);
 int ns_engine_coalescer_stop(ns_engine* e);
 int ns_engine_coalescer_stats(ns_engine* e, uint64_t* batches, uint64_t* queries, uint64_t* max_batch_seen);
+/* Load generator (bench tooling): nthreads host threads x per_thread blocking ns_engine_search_one calls over the Q
+ * NUL-separated queries in zqueries; reports queries/s and the p50 / p99 latency of one call in microseconds. */
+int ns_engine_load_test(ns_engine* e, uint32_t nthreads, uint32_t per_thread, uint32_t Q, const char* zqueries,
+                        size_t nbytes, int k, double* qps, double* p50_us, double* p99_us);
 /* cord_uid of (segment, doc); returns length or -1 */
 int ns_engine_cord_uid(const ns_engine* e, uint32_t seg, uint32_t doc, char* buf, size_t cap);
 

@@ -102,6 +102,8 @@ SYMBOLS = {
     "ns_engine_coalescer_start": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_int]),
     "ns_engine_coalescer_stop": (C.c_int, [_P]),
     "ns_engine_coalescer_stats": (C.c_int, [_P, _u64p, _u64p, _u64p]),
+    "ns_engine_load_test": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_char_p, C.c_size_t, C.c_int,
+                                      C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "ns_engine_destroy": (None, [_P]),
     "ns_engine_set_shard": (C.c_int, [_P, C.c_int, C.c_int]),
     "ns_engine_reload": (C.c_int, [_P]),

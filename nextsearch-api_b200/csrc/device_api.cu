@@ -223,7 +223,7 @@ struct ns_exchange {
     };
     std::vector<Dest> dests;
     bool receiver = false;    // this rank is one of its own destinations: it waits for all ranks and merges
-    uint64_t timeout_ns = 2000000000ull;
+    uint64_t timeout_ns = 10000000000ull;  // NSB200_EXCHANGE_TIMEOUT_MS, default 10 s
     uint8_t* h_out = nullptr; // pinned, stride + 256 bytes
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_done[8] = {};  // per slot: merge of the last step using the slot has been enqueued
@@ -251,22 +251,28 @@ struct KernelCfg {
     int threads = kThreads;
 };
 
-template <int TDW, int KCAP, bool FAST, bool IMPACT, int NG>
+template <int TDW, int KCAP, bool FAST, bool IMPACT, int NG, bool PUB>
 KernelCfg cfg_of() {
-    return KernelCfg{(const void*)bm25_score_topk_kernel<TDW, KCAP, FAST, IMPACT, NG>,
+    return KernelCfg{(const void*)bm25_score_topk_kernel<TDW, KCAP, FAST, IMPACT, NG, PUB>,
                      sizeof(WarpSmem<TDW, KCAP>) * kWarpsPerBlock};
 }
 
-template <int TDW, int KCAP, int NG>
+template <int TDW, int KCAP, int NG, bool PUB>
 KernelCfg pick_kernel_tk(bool fast, bool impact) {
-    if (fast) return impact ? cfg_of<TDW, KCAP, true, true, NG>() : cfg_of<TDW, KCAP, true, false, NG>();
-    return impact ? cfg_of<TDW, KCAP, false, true, NG>() : cfg_of<TDW, KCAP, false, false, NG>();
+    if (fast) return impact ? cfg_of<TDW, KCAP, true, true, NG, PUB>() : cfg_of<TDW, KCAP, true, false, NG, PUB>();
+    return impact ? cfg_of<TDW, KCAP, false, true, NG, PUB>() : cfg_of<TDW, KCAP, false, false, NG, PUB>();
+}
+
+template <bool PUB>
+KernelCfg pick_kernel_p(uint32_t k, bool fast, bool impact, bool wide) {
+    if (wide) return k <= 16 ? pick_kernel_tk<kTileDocs, 16, 2, PUB>(fast, impact) : pick_kernel_tk<kTileDocs, 104, 2, PUB>(fast, impact);
+    return k <= 16 ? pick_kernel_tk<kTileDocs, 16, 1, PUB>(fast, impact) : pick_kernel_tk<kTileDocs, 104, 1, PUB>(fast, impact);
 }
 
 // wide: some (query, segment) has more than 32 terms (two 32-term register groups per lane)
-KernelCfg pick_kernel(uint32_t k, bool fast, bool impact, bool wide) {
-    if (wide) return k <= 16 ? pick_kernel_tk<kTileDocs, 16, 2>(fast, impact) : pick_kernel_tk<kTileDocs, 104, 2>(fast, impact);
-    return k <= 16 ? pick_kernel_tk<kTileDocs, 16, 1>(fast, impact) : pick_kernel_tk<kTileDocs, 104, 1>(fast, impact);
+// pub:  the score kernel publishes finished queries to peer GPUs (multi-GPU exchange)
+KernelCfg pick_kernel(uint32_t k, bool fast, bool impact, bool wide, bool pub) {
+    return pub ? pick_kernel_p<true>(k, fast, impact, wide) : pick_kernel_p<false>(k, fast, impact, wide);
 }
 
 // The dynamic shared-memory opt-in and the occupancy query of every kernel variant, done once per index
@@ -276,8 +282,8 @@ int init_kernel_table(IndexShared* idx) {
     for (int kk = 0; kk < 2; kk++)
         for (int fast = 0; fast < 2; fast++)
             for (int impact = 0; impact < 2; impact++)
-                for (int wide = 0; wide < 2; wide++) {
-                    const KernelCfg cfg = pick_kernel(kk ? 100u : 10u, fast != 0, impact != 0, wide != 0);
+                for (int wp = 0; wp < 4; wp++) {
+                    const KernelCfg cfg = pick_kernel(kk ? 100u : 10u, fast != 0, impact != 0, (wp & 1) != 0, (wp & 2) != 0);
                     int per_sm = 0;
                     NS_CUDA(cudaFuncSetAttribute(cfg.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
                     NS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cfg.fn, cfg.threads, cfg.smem));
@@ -1034,7 +1040,7 @@ int launch_score(ns_batch* b, cudaStream_t s, const PublishDest* d_pub, uint32_t
         a.q_done = b->d_qdone;
         a.n_published = b->d_npub;
         const bool fast = b->fast && !b->owner->tun.no_fast;
-        const KernelCfg cfg = pick_kernel(b->k, fast, b->impact, b->max_in_seg > 32u);
+        const KernelCfg cfg = pick_kernel(b->k, fast, b->impact, b->max_in_seg > 32u, d_pub != nullptr);
         const uint32_t warps_per_block = (uint32_t)cfg.threads / 32u;
         int per_sm = 0;
         {

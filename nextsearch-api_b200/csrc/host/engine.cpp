@@ -86,6 +86,7 @@ struct ns_engine {
     std::vector<int> devices;       // CUDA ordinals, empty = host-only engine
     std::vector<ns_index*> idx;     // one per device slot
     int rank = 0, world = 1;        // process-level share: segment i is owned when i % world == rank
+    bool trace = false;             // NSB200_TRACE (read at create): per-phase host timings of every search on stderr
     bool keep_raw = false;          // NSB200_KEEP_RAW (read at create): keep {docId, tf} next to the resident scores, so that
                                     // batches through the raw ABI may name a row with a foreign idf
     std::mutex gen_mu;              // guards `gen` (the pointer only)
@@ -399,16 +400,25 @@ int search_core(ns_engine* e, const std::shared_ptr<const Generation>& gen, uint
     for (size_t d = 0; d < ndev; d++) colsets.push_back(&g.dev_cols[d]);
     std::vector<Resolved> parts;
     std::vector<uint8_t> has;
+    using clk = std::chrono::steady_clock;
+    const auto t0 = clk::now();
     resolve_all(e, g, Q, terms_of, colsets, parts, has);
     if (has_found && Q) std::memcpy(has_found, has.data(), Q);
+    const auto t1 = clk::now();
+    auto ms = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
 
     if (ndev == 1) {
         ns_batch* b = nullptr;
         int rc = batch_prepare_on(e->idx[0], g.dev_state[0], Q, k, parts[0].q_off.data(), parts[0].terms.data(), &b);
         if (rc != NS_OK) return rc;
+        const auto t2 = clk::now();
         rc = ns_batch_launch(b, nullptr);
         if (rc == NS_OK) rc = ns_batch_fetch(b, out_hits, out_nhits, out_found);
+        const auto t3 = clk::now();
         ns_batch_destroy(b);
+        if (e->trace)
+            std::fprintf(stderr, "[nsb200] Q=%u resolve %.3f ms, prepare %.3f, launch+fetch %.3f, destroy %.3f\n", Q, ms(t0, t1),
+                         ms(t1, t2), ms(t2, t3), ms(t3, clk::now()));
         return rc;
     }
 
@@ -427,6 +437,7 @@ int search_core(ns_engine* e, const std::shared_ptr<const Generation>& gen, uint
         if (rcs[d] != NS_OK) errs[d] = ns_last_error();
     };
     e->workers().run((int)ndev, one);
+    const auto t2 = clk::now();
     for (size_t d = 0; d < ndev && rc == NS_OK; d++)
         if (rcs[d] != NS_OK) {
             rc = rcs[d];
@@ -434,9 +445,13 @@ int search_core(ns_engine* e, const std::shared_ptr<const Generation>& gen, uint
         }
     if (rc == NS_OK) rc = exchange_root_merge(grp->x[0], bs.data(), (int)ndev, step, Q, k);
     if (rc == NS_OK) rc = ns_exchange_fetch(grp->x[0], step, Q, k, out_hits, out_nhits, out_found);
+    const auto t3 = clk::now();
     std::string keep = rc != NS_OK ? std::string(ns_last_error()) : std::string();
     for (auto* b : bs)
         if (b) ns_batch_destroy(b);  // waits for that device's kernels
+    if (e->trace)
+        std::fprintf(stderr, "[nsb200] Q=%u ndev=%zu resolve %.3f ms, prepare+launch %.3f, merge+fetch %.3f, destroy %.3f\n", Q, ndev,
+                     ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, clk::now()));
     if (rc == NS_OK) release_group(e, std::move(grp));  // a failed group is dropped: its flags may be in any state
     else set_error(keep);
     return rc;
@@ -607,6 +622,7 @@ extern "C" int ns_engine_create_multi(const char* index_dir, int ndev, const int
     auto e = std::make_unique<ns_engine>();
     e->index_dir = index_dir;
     e->keep_raw = std::getenv("NSB200_KEEP_RAW") != nullptr;
+    e->trace = std::getenv("NSB200_TRACE") != nullptr;
     for (int d = 0; d < ndev; d++) {
         // (the same ordinal may be listed more than once: two device slots on one GPU — how the
         //  multi-device path is exercised on a single-GPU box)
@@ -887,6 +903,56 @@ extern "C" int ns_engine_coalescer_stats(ns_engine* e, uint64_t* batches, uint64
     if (batches) *batches = e->coalescer ? e->coalescer->n_batches.load() : 0;
     if (queries) *queries = e->coalescer ? e->coalescer->n_queries.load() : 0;
     if (max_batch_seen) *max_batch_seen = e->coalescer ? e->coalescer->max_seen.load() : 0;
+    return NS_OK;
+}
+
+// Load generator (bench tooling): `nthreads` host threads each issue `per_thread` blocking ns_engine_search_one
+// calls — the traffic shape of the reference's HTTP workers (src/api_server.cpp:117-178) without Python in the
+// loop.  Thread t starts at query (t * per_thread) % Q and walks the Q given queries cyclically.
+extern "C" int ns_engine_load_test(ns_engine* e, uint32_t nthreads, uint32_t per_thread, uint32_t Q, const char* zqueries,
+                                   size_t nbytes, int k, double* qps, double* p50_us, double* p99_us) {
+    if (!e || !zqueries || Q == 0 || nthreads == 0 || per_thread == 0) { set_error("ns_engine_load_test: bad argument"); return NS_ERR_INVALID; }
+    std::vector<const char*> starts;
+    if (!split_packed(zqueries, nbytes, Q, starts)) { set_error("ns_engine_load_test: fewer than Q strings"); return NS_ERR_INVALID; }
+    const int K = std::max(1, std::min(k, NS_MAX_K));
+    std::vector<std::vector<double>> lat(nthreads);
+    std::atomic<int> failed{NS_OK};
+    std::vector<std::string> errs(nthreads);
+    std::vector<std::thread> th;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (uint32_t t = 0; t < nthreads; t++) {
+        th.emplace_back([&, t] {
+            std::vector<ns_hit> hits((size_t)K);
+            uint32_t nh;
+            uint64_t fo;
+            uint8_t has;
+            lat[t].reserve(per_thread);
+            for (uint32_t i = 0; i < per_thread; i++) {
+                const char* q = starts[((uint64_t)t * per_thread + i) % Q];
+                const auto a = std::chrono::steady_clock::now();
+                const int rc = ns_engine_search_one(e, q, K, hits.data(), &nh, &fo, &has);
+                if (rc != NS_OK) {
+                    failed = rc;
+                    errs[t] = ns_last_error();
+                    return;
+                }
+                lat[t].push_back(std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - a).count());
+            }
+        });
+    }
+    for (auto& x : th) x.join();
+    const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (failed != NS_OK) {
+        for (auto& m : errs)
+            if (!m.empty()) { set_error(m); break; }
+        return failed;
+    }
+    std::vector<double> all;
+    for (auto& v : lat) all.insert(all.end(), v.begin(), v.end());
+    std::sort(all.begin(), all.end());
+    if (qps) *qps = secs > 0 ? (double)all.size() / secs : 0.0;
+    if (p50_us) *p50_us = all.empty() ? 0.0 : all[all.size() / 2];
+    if (p99_us) *p99_us = all.empty() ? 0.0 : all[(size_t)((double)(all.size() - 1) * 0.99)];
     return NS_OK;
 }
 

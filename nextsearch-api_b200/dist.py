@@ -1,13 +1,21 @@
-"""Segment-sharded search over the GPUs of one box.
+"""Segment-sharded search with ONE PROCESS PER GPU (torchrun / torch.distributed).
 
-One process per GPU (torch.distributed, NCCL).  Segment i lives on rank i % world; every rank
-receives the same query batch, scores its own segments, and the per-rank result blobs
-(hits | nhits | found) are exchanged with ONE all-gather per batch and merged on every rank by
-ns_merge_blobs_device under the total order (score desc, segment asc, docId asc).  Scores are
-segment-local in the reference (src/api_engine.cpp:461,478), so no other exchange exists.
+Segment i lives on rank i % world; every rank receives the same query batch and scores its own segments.
+What crosses GPUs is only what the reference keeps across segments — the global top-K and the found sum
+(src/api_engine.cpp:435,495).  The exchange is fused into the score kernel (ns_exchange, C ABI): each rank's
+kernel stores every finished query's list straight into all peers' gather buffers over NVLink (CUDA IPC
+mappings of the peers' buffers), raises a flag, and every rank merges the `world` blobs under the total
+order (score desc, segment asc, docId asc).  torch.distributed is plumbing here: rendezvous, the one-time
+exchange of the 64-byte IPC handles, barriers.  If the IPC mapping cannot be set up (e.g. no peer access
+between two GPUs) the ranks agree to fall back to one NCCL all-gather of the result blobs per batch followed
+by the same merge kernel.
+
+The single-process alternative — one engine handle spanning all GPUs of the box, which is what a C++
+api_server would link — is ``Engine(index_dir, devices=[...])`` (ns_engine_create_multi).
 """
 from __future__ import annotations
 
+import ctypes as C
 from dataclasses import dataclass
 from typing import Optional, Sequence, Tuple
 
@@ -15,9 +23,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import check
-from .engine import HIT_DTYPE, Batch, BatchResult, Engine, clamp_k
-
-import ctypes as C
+from .engine import HIT_DTYPE, Batch, BatchResult, Engine, Exchange, clamp_k
 
 _ALIGN = 256
 
@@ -71,100 +77,118 @@ class ShardedBatch:
     has_found: np.ndarray
     Q: int
     k: int
-    local_blob: "object"      # torch uint8 view of the batch's device result blob
-    gathered: "object"        # torch uint8 [world * blob_bytes]
-    out: "object"             # torch uint8 [blob_bytes]: merged hits | nhits | found (same layout as a rank blob)
-    blob_bytes: int
-    off_n: int
-    off_f: int
-    comm_done: "object" = None  # torch event: this batch's all-gather + merge have finished (exchange stream)
+    step: int = -1                 # exchange step of the last launch
+    # NCCL fallback only
+    local_blob: "object" = None    # torch uint8 view of the batch's device result blob
+    gathered: "object" = None      # torch uint8 [world * blob_bytes]
+    out: "object" = None           # torch uint8 [blob_bytes]: merged hits | nhits | found
+    blob_bytes: int = 0
+    off_n: int = 0
+    off_f: int = 0
 
 
 class ShardedSearcher:
-    def __init__(self, index_dir: str, device: int, rank: int, world: int, group=None):
+    """mode: "peer" (default; falls back to "nccl" if the IPC set-up fails on any rank) or "nccl"."""
+
+    def __init__(self, index_dir: str, device: int, rank: int, world: int, group=None, max_queries: int = 4096,
+                 mode: str = "peer"):
         import torch
         import torch.distributed as dist
 
         self.torch, self.dist = torch, dist
         self.rank, self.world, self.device, self.group = rank, world, device, group
         self.engine = Engine(index_dir, device=device, rank=rank, world=world)
-        self.comm_stream = None  # exchange stream (all-gather + merge), created on first sharded launch
-        self._last_comm = None
+        self.exchange: Optional[Exchange] = None
+        self.step = 0
+        self.mode = "single" if world == 1 else mode
+        if world > 1 and mode == "peer":
+            ok = 1
+            try:
+                self.exchange = Exchange(device, world, rank, max_queries, slots=2)
+                mine = self.exchange.ipc_handle()
+            except Exception:  # noqa: BLE001
+                ok, mine = 0, b""
+            handles = [None] * world
+            dist.all_gather_object(handles, mine, group=group)
+            if ok and all(handles):
+                try:
+                    for p in range(world):
+                        if p == rank:
+                            self.exchange.attach(self.exchange)
+                        else:
+                            self.exchange.attach_ipc(p, handles[p])
+                except Exception:  # noqa: BLE001
+                    ok = 0
+            else:
+                ok = 0
+            oks = [None] * world
+            dist.all_gather_object(oks, ok, group=group)  # every rank takes the same path
+            if not all(oks):
+                self.exchange = None
+                self.mode = "nccl"
 
     def reload(self) -> bool:
         return self.engine.reload()
 
     def prepare(self, queries: Sequence[str], k: int) -> ShardedBatch:
-        torch = self.torch
         q_off, terms, has = self.engine.resolve_batch(queries)
         b = self.engine.index.prepare(q_off, terms, k)
-        lib = _lib.load()
-        ptr, nbytes, off_n, off_f = C.c_void_p(), C.c_uint64(), C.c_uint64(), C.c_uint64()
-        check(lib.ns_batch_result_blob(b._h, C.byref(ptr), C.byref(nbytes), C.byref(off_n), C.byref(off_f)))
-        dev = torch.device("cuda", self.device)
-        local = torch.as_tensor(_DevMem(ptr.value, nbytes.value), device=dev)
-        Q, K = len(queries), clamp_k(k)
-        return ShardedBatch(
-            batch=b, has_found=has, Q=Q, k=K, local_blob=local,
-            gathered=torch.empty(self.world * nbytes.value, dtype=torch.uint8, device=dev),
-            out=torch.empty(nbytes.value, dtype=torch.uint8, device=dev),
-            blob_bytes=nbytes.value, off_n=off_n.value, off_f=off_f.value)
+        sb = ShardedBatch(batch=b, has_found=has, Q=len(queries), k=clamp_k(k))
+        if self.mode == "nccl":
+            torch = self.torch
+            lib = _lib.load()
+            ptr, nbytes, off_n, off_f = C.c_void_p(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+            check(lib.ns_batch_result_blob(b._h, C.byref(ptr), C.byref(nbytes), C.byref(off_n), C.byref(off_f)))
+            dev = torch.device("cuda", self.device)
+            sb.local_blob = torch.as_tensor(_DevMem(ptr.value, nbytes.value), device=dev)
+            sb.gathered = torch.empty(self.world * nbytes.value, dtype=torch.uint8, device=dev)
+            sb.out = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+            sb.blob_bytes, sb.off_n, sb.off_f = nbytes.value, off_n.value, off_f.value
+        return sb
 
-    def launch(self, sb: ShardedBatch) -> None:
-        """score+top-k on this rank's segments (torch's current stream) -> all-gather -> merge.
-
-        With more than one rank the exchange (NCCL all-gather of the result blobs + device merge) runs on
-        its own stream behind an event, so the NEXT batch's score kernel — which does not depend on it —
-        is not held back by the latency-bound collective: the exchange of batch i lands in the tail of the
-        score kernel of batch i+1, where SMs are idle anyway.  `fetch` / `drain` order later work after it."""
-        torch, dist = self.torch, self.dist
-        cur = torch.cuda.current_stream(self.device)
-        # torch's default stream has handle 0, which ns_batch_launch reads as "the batch's own stream";
-        # name it explicitly (cudaStreamLegacy == 0x1) so that everything is ordered on torch's streams
-        stream = cur.cuda_stream or 1
-        if sb.comm_done is not None:
-            cur.wait_event(sb.comm_done)  # the previous exchange of this batch still reads its result blob
-        sb.batch.launch(stream)
-        lib = _lib.load()
-        base = sb.out.data_ptr()
-        if self.world == 1:
-            check(lib.ns_merge_blobs_device(self.device, sb.Q, sb.k, 1, C.c_void_p(sb.local_blob.data_ptr()),
-                                            sb.blob_bytes, sb.off_n, sb.off_f, C.c_void_p(base),
-                                            C.c_void_p(base + sb.off_n), C.c_void_p(base + sb.off_f), C.c_void_p(stream)))
+    def launch(self, sb: ShardedBatch, stream: Optional[int] = None) -> None:
+        """Score this rank's segments and merge with the other ranks' results; everything is enqueued on ONE
+        stream (`stream`, default torch's current one), which is what makes two exchange slots sufficient.
+        Collective: every rank must launch the same batches in the same order.  A batch's result must be
+        fetched before the batch two launches later is launched (two slots)."""
+        torch = self.torch
+        if stream is None:
+            # torch's default stream has handle 0, which the C ABI reads as "the batch's own stream";
+            # name it explicitly (cudaStreamLegacy == 0x1)
+            stream = torch.cuda.current_stream(self.device).cuda_stream or 1
+        if self.mode == "single":
+            sb.batch.launch(stream)
             return
-        if self.comm_stream is None:
-            self.comm_stream = torch.cuda.Stream(device=self.device)
-        cs = self.comm_stream
-        scored = torch.cuda.Event()
-        scored.record(cur)
-        cs.wait_event(scored)
-        with torch.cuda.stream(cs):
-            dist.all_gather_into_tensor(sb.gathered, sb.local_blob, group=self.group)
-            check(lib.ns_merge_blobs_device(self.device, sb.Q, sb.k, self.world, C.c_void_p(sb.gathered.data_ptr()),
-                                            sb.blob_bytes, sb.off_n, sb.off_f, C.c_void_p(base),
-                                            C.c_void_p(base + sb.off_n), C.c_void_p(base + sb.off_f),
-                                            C.c_void_p(cs.cuda_stream)))
-            sb.comm_done = torch.cuda.Event()
-            sb.comm_done.record(cs)
-        sb.gathered.record_stream(cs)
-        sb.out.record_stream(cs)
-        self._last_comm = sb.comm_done
-
-    def drain(self) -> None:
-        """Order torch's current stream after every exchange launched so far."""
-        if self._last_comm is not None:
-            self.torch.cuda.current_stream(self.device).wait_event(self._last_comm)
+        if self.mode == "peer":
+            sb.step = self.step
+            self.step += 1
+            self.exchange.launch(sb.batch, sb.step, stream)
+            self.exchange.merge(sb.step, sb.Q, sb.k, spin=True, stream=stream)
+            return
+        # NCCL fallback: all-gather of the blobs on the launching stream, then the merge kernel
+        lib = _lib.load()
+        sb.batch.launch(stream)
+        ext = torch.cuda.ExternalStream(stream, device=self.device) if stream not in (0, 1) else torch.cuda.default_stream(self.device)
+        with torch.cuda.stream(ext):
+            self.dist.all_gather_into_tensor(sb.gathered, sb.local_blob, group=self.group)
+        base = sb.out.data_ptr()
+        check(lib.ns_merge_blobs_device(self.device, sb.Q, sb.k, self.world, C.c_void_p(sb.gathered.data_ptr()), sb.blob_bytes,
+                                        sb.off_n, sb.off_f, C.c_void_p(base), C.c_void_p(base + sb.off_n),
+                                        C.c_void_p(base + sb.off_f), C.c_void_p(stream)))
 
     def fetch(self, sb: ShardedBatch) -> BatchResult:
-        if sb.comm_done is not None:
-            self.torch.cuda.current_stream(self.device).wait_event(sb.comm_done)
-        hits, nhits, found = unpack_blob(sb.out.cpu().numpy(), sb.Q, sb.k)  # one D2H copy
+        if self.mode == "single":
+            hits, nhits, found = sb.batch.fetch()
+        elif self.mode == "peer":
+            hits, nhits, found = self.exchange.fetch(sb.step, sb.Q, sb.k)
+        else:
+            self.torch.cuda.current_stream(self.device).synchronize()
+            hits, nhits, found = unpack_blob(sb.out.cpu().numpy(), sb.Q, sb.k)
         return BatchResult(hits, nhits, found, sb.has_found, sb.k)
 
     def search_many(self, batches: Sequence[Sequence[str]], k: int = 10):
         """Several query batches, one result each, with the host front end of batch i+1 (tokenise, lexicon,
-        prepare, H2D) running while the GPU works on batch i.  Every rank must call it with the same batches
-        (one collective per batch, issued in the same order everywhere)."""
+        prepare, H2D) running while the GPUs work on batch i.  Every rank must call it with the same batches."""
         out, prev = [], None
         for qs in batches:
             sb = self.prepare(qs, k)
@@ -184,3 +208,9 @@ class ShardedSearcher:
         res = self.fetch(sb)
         sb.batch.close()
         return res
+
+    def close(self) -> None:
+        if self.exchange is not None:
+            self.exchange.close()
+            self.exchange = None
+        self.engine.close()

@@ -93,6 +93,14 @@ class Batch:
     def num_launches(self) -> int:
         return int(self._lib.ns_batch_num_launches(self._h))
 
+    @property
+    def upload_bytes(self) -> int:
+        return int(self._lib.ns_batch_upload_bytes(self._h))
+
+    @property
+    def result_bytes(self) -> int:
+        return int(self._lib.ns_batch_result_bytes(self._h))
+
     def kernel_ms(self, which: int = 0) -> float:
         return float(self._lib.ns_batch_last_kernel_ms(self._h, which))
 
@@ -457,6 +465,14 @@ class Engine:
         b, q, m = C.c_uint64(), C.c_uint64(), C.c_uint64()
         check(self._lib.ns_engine_coalescer_stats(self._h, C.byref(b), C.byref(q), C.byref(m)))
         return {"batches": b.value, "queries": q.value, "max_batch": m.value}
+
+    def load_test(self, queries: Sequence[str], nthreads: int, per_thread: int, k: int = 10) -> dict:
+        """ns_engine_load_test: nthreads native threads x per_thread blocking single-query calls."""
+        z = ("\0".join(queries) + "\0").encode("utf-8")
+        qps, p50, p99 = C.c_double(), C.c_double(), C.c_double()
+        check(self._lib.ns_engine_load_test(self._h, int(nthreads), int(per_thread), len(queries), z, len(z), int(k),
+                                            C.byref(qps), C.byref(p50), C.byref(p99)))
+        return {"qps": qps.value, "p50_us": p50.value, "p99_us": p99.value, "threads": nthreads, "calls": nthreads * per_thread}
 
     def reload_stats(self) -> dict:
         t, r, d = C.c_double(), C.c_double(), C.c_double()

@@ -21,7 +21,7 @@ def test_workload_config_names_the_baseline_configs():
 
 def test_roofline_traffic_comes_from_the_committed_ncu_capture():
     bench = importlib.import_module("bench")
-    assert os.path.exists(bench.NCU_SUMMARY), "bench.py quotes a profile that is not committed"
+    assert os.path.exists(bench.ncu_summary_path()), "bench.py quotes a profile that is not committed"
     t = bench.ncu_traffic()
     # DRAM read+write of one score-kernel launch: well below the 6.11 GB of algorithmic bytes (L2 sharing)
     assert t is not None and 1e8 < t < 6.11e9
