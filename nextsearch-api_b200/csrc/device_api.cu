@@ -791,6 +791,102 @@ size_t build_items(ns_batch* b, uint32_t forced) {
 
 }  // namespace
 
+namespace {
+
+// Second half of every prepare: sizes the batch's device blob, fills the pinned input blob, builds the items and
+// starts the upload.  `kept` are the batch's terms in kernel form; dist/dstart describe the terms whose scores are
+// not resident (empty on the engine's trusted path).
+int finish_prepare(ns_index* idx, const std::shared_ptr<IndexState>& st, std::unique_ptr<ns_batch> b, uint32_t Q, uint32_t k,
+                   const DevTerm* kept, size_t nkept, const uint32_t* qoff32, const std::vector<DevDistinct>& dist,
+                   const std::vector<uint32_t>& dstart, uint64_t dist_post, uint64_t total_post, uint64_t nonres_post,
+                   uint64_t n_resident, uint32_t max_in_seg, bool scan_always, bool fast, bool all_raw, ns_batch** out) {
+    b->owner = idx->sh;
+    b->st = st;
+    b->Q = Q;
+    b->k = k;
+    b->nterms = nkept;
+    b->postings = total_post;
+    b->scan_always = scan_always;
+    b->max_in_seg = max_in_seg;
+    b->fast = fast && !scan_always;
+    b->ndist = (uint32_t)dist.size();
+    b->dist_postings = dist_post;
+    // Share term scores across the batch when that removes enough evaluations: the pre-pass reads
+    // and writes every distinct posting once, the scoring kernel then skips ~2/3 of its arithmetic.
+    // Segments without raw postings can only be scored from impacts.
+    {
+        const double share = dist_post ? (double)nonres_post / (double)dist_post : 0.0;
+        const int env = idx->sh->tun.impact;
+        b->impact = !all_raw || n_resident > 0 || (env >= 0 ? (env != 0 && dist_post > 0) : (share >= 1.5));
+    }
+
+    const size_t tiles = std::max<uint32_t>(1, st->total_tiles);
+    b->items_cap = (size_t)Q * std::min<size_t>(tiles, kMaxSplit);
+    const size_t sz_qoff = align_up(((size_t)Q + 1) * 4);
+    const size_t sz_terms = align_up(std::max<size_t>(1, nkept) * sizeof(DevTerm));
+    const size_t sz_dist = align_up(std::max<size_t>(1, dist.size()) * sizeof(DevDistinct));
+    const size_t sz_dstart = align_up(dstart.size() * 4);
+    const size_t sz_items = align_up(std::max<size_t>(1, b->items_cap) * sizeof(DevItem));
+    const size_t off_dist = sz_qoff + sz_terms;
+    const size_t off_dstart = off_dist + sz_dist;
+    b->off_items = off_dstart + sz_dstart;  // last uploaded region: only its used prefix is copied
+    const size_t in_cap = b->off_items + sz_items;
+    // zeroed per launch: queue head | locks[Q] | done[Q] | published | result blob
+    const size_t sz_ctrl = align_up((2 + 2 * (size_t)Q) * 4);
+    const size_t sz_hits = align_up(std::max<size_t>(1, (size_t)Q * k) * sizeof(ns_hit));
+    const size_t sz_n = align_up(std::max<size_t>(1, Q) * 4);
+    const size_t sz_found = align_up(std::max<size_t>(1, Q) * 8);
+    b->out_bytes = sz_hits + sz_n + sz_found;
+    b->off_n = sz_hits;
+    b->off_found = sz_hits + sz_n;
+    b->off_zero = in_cap;
+    b->zero_bytes = sz_ctrl + b->out_bytes;
+
+    int rc = acquire_res(idx->sh.get(), in_cap + b->zero_bytes, in_cap, b->out_bytes, b->res);
+    if (rc != NS_OK) return rc;
+    BatchRes& r = *b->res;
+    std::memcpy(r.h_in, qoff32, ((size_t)Q + 1) * 4);
+    if (nkept != 0) std::memcpy(r.h_in + sz_qoff, kept, nkept * sizeof(DevTerm));
+    if (!dist.empty()) std::memcpy(r.h_in + off_dist, dist.data(), dist.size() * sizeof(DevDistinct));
+    std::memcpy(r.h_in + off_dstart, dstart.data(), dstart.size() * 4);
+    b->d_dist = reinterpret_cast<DevDistinct*>(r.d_blob + off_dist);
+    b->d_dstart = reinterpret_cast<uint32_t*>(r.d_blob + off_dstart);
+    if (b->impact && dist_post) {
+        const size_t need = (dist_post + 4) * sizeof(uint2);
+        if (r.scratch_cap < need) {
+            if (r.d_scratch) cudaFree(r.d_scratch);
+            r.d_scratch = nullptr;
+            r.scratch_cap = 0;
+            size_t cap = 1 << 20;
+            while (cap < need) cap <<= 1;
+            NS_CUDA(cudaMalloc(&r.d_scratch, cap));
+            r.scratch_cap = cap;
+        }
+    }
+    const size_t items_bytes = build_items(b.get(), 0);
+    b->up_bytes = b->off_items + items_bytes;
+    b->d_qoff = reinterpret_cast<uint32_t*>(r.d_blob);
+    b->d_terms = reinterpret_cast<DevTerm*>(r.d_blob + sz_qoff);
+    b->d_items = reinterpret_cast<DevItem*>(r.d_blob + b->off_items);
+    uint32_t* ctrl = reinterpret_cast<uint32_t*>(r.d_blob + b->off_zero);
+    b->d_counter = ctrl;
+    b->d_npub = ctrl + 1;
+    b->d_qlock = ctrl + 2;
+    b->d_qdone = ctrl + 2 + Q;
+    b->d_out = r.d_blob + b->off_zero + sz_ctrl;
+    b->d_out_hits = reinterpret_cast<ns_hit*>(b->d_out);
+    b->d_out_n = reinterpret_cast<uint32_t*>(b->d_out + b->off_n);
+    b->d_out_found = reinterpret_cast<unsigned long long*>(b->d_out + b->off_found);
+    // The upload is NOT waited for here: launches on any stream order themselves after ev_h2d, so the
+    // caller's host thread goes on (to the launch, or to preparing the next batch) while the copy runs.
+    NS_CUDA(cudaMemcpyAsync(r.d_blob, r.h_in, b->up_bytes, cudaMemcpyHostToDevice, r.stream));
+    NS_CUDA(cudaEventRecord(r.ev_h2d, r.stream));
+    *out = b.release();
+    return NS_OK;
+}
+
+}  // namespace
+
 int nsb::batch_prepare_on(ns_index* idx, const std::shared_ptr<const void>& state, uint32_t Q, int k_in,
                           const uint64_t* q_off, const ns_qterm* terms, ns_batch** out) {
     if (!idx || !out || !q_off || (Q && q_off[Q] && !terms)) { set_error("ns_batch_prepare: null argument"); return NS_ERR_INVALID; }
@@ -894,90 +990,34 @@ int nsb::batch_prepare_on(ns_index* idx, const std::shared_ptr<const void>& stat
         total_post += b->weight[q];
     }
 
-    b->owner = idx->sh;
-    b->st = st;
-    b->Q = Q;
-    b->k = k;
-    b->nterms = kept.size();
-    b->postings = total_post;
-    b->scan_always = scan_always;
-    b->max_in_seg = max_in_seg;
-    b->fast = fast && !scan_always;
     dstart.push_back((uint32_t)dist_post);
-    b->ndist = (uint32_t)dist.size();
-    b->dist_postings = dist_post;
-    // Share term scores across the batch when that removes enough evaluations: the pre-pass reads
-    // and writes every distinct posting once, the scoring kernel then skips ~2/3 of its arithmetic.
-    // Segments without raw postings can only be scored from impacts.
-    {
-        const double share = dist_post ? (double)nonres_post / (double)dist_post : 0.0;
-        const int env = idx->sh->tun.impact;
-        b->impact = !all_raw || n_resident > 0 || (env >= 0 ? (env != 0 && dist_post > 0) : (share >= 1.5));
-    }
+    return finish_prepare(idx, st, std::move(b), Q, k, kept.data(), kept.size(), qoff32.data(), dist, dstart, dist_post, total_post,
+                          nonres_post, n_resident, max_in_seg, scan_always, fast, all_raw, out);
+}
 
-    const size_t tiles = std::max<uint32_t>(1, st->total_tiles);
-    b->items_cap = (size_t)Q * std::min<size_t>(tiles, kMaxSplit);
-    const size_t sz_qoff = align_up(((size_t)Q + 1) * 4);
-    const size_t sz_terms = align_up(std::max<size_t>(1, kept.size()) * sizeof(DevTerm));
-    const size_t sz_dist = align_up(std::max<size_t>(1, dist.size()) * sizeof(DevDistinct));
-    const size_t sz_dstart = align_up(dstart.size() * 4);
-    const size_t sz_items = align_up(std::max<size_t>(1, b->items_cap) * sizeof(DevItem));
-    const size_t off_dist = sz_qoff + sz_terms;
-    const size_t off_dstart = off_dist + sz_dist;
-    b->off_items = off_dstart + sz_dstart;  // last uploaded region: only its used prefix is copied
-    const size_t in_cap = b->off_items + sz_items;
-    // zeroed per launch: queue head | locks[Q] | done[Q] | published | result blob
-    const size_t sz_ctrl = align_up((2 + 2 * (size_t)Q) * 4);
-    const size_t sz_hits = align_up(std::max<size_t>(1, (size_t)Q * k) * sizeof(ns_hit));
-    const size_t sz_n = align_up(std::max<size_t>(1, Q) * 4);
-    const size_t sz_found = align_up(std::max<size_t>(1, Q) * 8);
-    b->out_bytes = sz_hits + sz_n + sz_found;
-    b->off_n = sz_hits;
-    b->off_found = sz_hits + sz_n;
-    b->off_zero = in_cap;
-    b->zero_bytes = sz_ctrl + b->out_bytes;
-
-    int rc = acquire_res(idx->sh.get(), in_cap + b->zero_bytes, in_cap, b->out_bytes, b->res);
-    if (rc != NS_OK) return rc;
-    BatchRes& r = *b->res;
-    std::memcpy(r.h_in, qoff32.data(), ((size_t)Q + 1) * 4);
-    if (!kept.empty()) std::memcpy(r.h_in + sz_qoff, kept.data(), kept.size() * sizeof(DevTerm));
-    if (!dist.empty()) std::memcpy(r.h_in + off_dist, dist.data(), dist.size() * sizeof(DevDistinct));
-    std::memcpy(r.h_in + off_dstart, dstart.data(), dstart.size() * 4);
-    b->d_dist = reinterpret_cast<DevDistinct*>(r.d_blob + off_dist);
-    b->d_dstart = reinterpret_cast<uint32_t*>(r.d_blob + off_dstart);
-    if (b->impact && dist_post) {
-        const size_t need = (dist_post + 4) * sizeof(uint2);
-        if (r.scratch_cap < need) {
-            if (r.d_scratch) cudaFree(r.d_scratch);
-            r.d_scratch = nullptr;
-            r.scratch_cap = 0;
-            size_t cap = 1 << 20;
-            while (cap < need) cap <<= 1;
-            NS_CUDA(cudaMalloc(&r.d_scratch, cap));
-            r.scratch_cap = cap;
-        }
+int nsb::batch_prepare_trusted(ns_index* idx, const std::shared_ptr<const void>& state, uint32_t Q, int k_in,
+                               const PreparedBatch& pb, ns_batch** out) {
+    static_assert(sizeof(PreparedTerm) == sizeof(DevTerm), "PreparedTerm mirrors DevTerm");
+    if (!idx || !out || !pb.qoff || (Q && !pb.weight) || (Q && pb.qoff[Q] && !pb.terms)) { set_error("batch_prepare_trusted: null argument"); return NS_ERR_INVALID; }
+    *out = nullptr;
+    std::shared_ptr<IndexState> st = std::const_pointer_cast<IndexState>(std::static_pointer_cast<const IndexState>(state));
+    if (!st) { set_error("ns_batch_prepare: index has no committed segments"); return NS_ERR_STATE; }
+    bool fast = pb.unit_weights;
+    for (auto& sg : st->segs) {
+        if (!sg.d_imp && sg.P) { set_error("batch_prepare_trusted: a segment has no resident scores"); return NS_ERR_STATE; }
+        fast = fast && sg.norm_in_range;
     }
-    const size_t items_bytes = build_items(b.get(), 0);
-    b->up_bytes = b->off_items + items_bytes;
-    b->d_qoff = reinterpret_cast<uint32_t*>(r.d_blob);
-    b->d_terms = reinterpret_cast<DevTerm*>(r.d_blob + sz_qoff);
-    b->d_items = reinterpret_cast<DevItem*>(r.d_blob + b->off_items);
-    uint32_t* ctrl = reinterpret_cast<uint32_t*>(r.d_blob + b->off_zero);
-    b->d_counter = ctrl;
-    b->d_npub = ctrl + 1;
-    b->d_qlock = ctrl + 2;
-    b->d_qdone = ctrl + 2 + Q;
-    b->d_out = r.d_blob + b->off_zero + sz_ctrl;
-    b->d_out_hits = reinterpret_cast<ns_hit*>(b->d_out);
-    b->d_out_n = reinterpret_cast<uint32_t*>(b->d_out + b->off_n);
-    b->d_out_found = reinterpret_cast<unsigned long long*>(b->d_out + b->off_found);
-    // The upload is NOT waited for here: launches on any stream order themselves after ev_h2d, so the
-    // caller's host thread goes on (to the launch, or to preparing the next batch) while the copy runs.
-    NS_CUDA(cudaMemcpyAsync(r.d_blob, r.h_in, b->up_bytes, cudaMemcpyHostToDevice, r.stream));
-    NS_CUDA(cudaEventRecord(r.ev_h2d, r.stream));
-    *out = b.release();
-    return NS_OK;
+    if (pb.max_in_seg > NS_MAX_TERMS) { set_error("ns_batch_prepare: more than NS_MAX_TERMS terms for one (query, segment)"); return NS_ERR_INVALID; }
+    NS_CUDA(cudaSetDevice(idx->device));
+    const uint32_t k = (uint32_t)std::max(1, std::min(k_in, NS_MAX_K));
+    auto b = std::make_unique<ns_batch>();
+    if (Q) b->weight.assign(pb.weight, pb.weight + Q);
+    uint64_t total_post = 0;
+    for (uint32_t q = 0; q < Q; q++) total_post += pb.weight[q];
+    const std::vector<DevDistinct> dist;
+    const std::vector<uint32_t> dstart(1, 0u);
+    return finish_prepare(idx, st, std::move(b), Q, k, reinterpret_cast<const DevTerm*>(pb.terms), pb.qoff[Q], pb.qoff, dist, dstart,
+                          0, total_post, 0, pb.qoff[Q], pb.max_in_seg, pb.scan_always, fast, false, out);
 }
 
 extern "C" int ns_batch_prepare(ns_index* idx, uint32_t Q, int k_in, const uint64_t* q_off, const ns_qterm* terms,

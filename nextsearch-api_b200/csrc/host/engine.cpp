@@ -337,6 +337,83 @@ void resolve_all(ns_engine* e, const Generation& g, uint32_t Q, TermsOf terms_of
     }
 }
 
+// The same pass in the device layer's own form (batch_prepare_trusted): per device, the terms as kernel
+// records with the slot the segment occupies on that device, the per-query posting totals and the batch flags —
+// everything the generic ns_batch_prepare would have to look up again per term.
+struct DevResolved {
+    std::vector<uint32_t> qoff;        // [Q+1]
+    std::vector<PreparedTerm> terms;
+    std::vector<uint64_t> weight;      // [Q]
+    uint32_t max_in_seg = 0;
+    bool unit = true, scan_always = false;
+};
+
+template <class TermsOf>
+void resolve_devices(ns_engine* e, const Generation& g, uint32_t Q, TermsOf terms_of, std::vector<DevResolved>& parts,
+                     std::vector<uint8_t>& has) {
+    const size_t np = g.dev_cols.size();
+    const size_t ncol = g.dict.owned.size();
+    WorkPool& pool = e->workers();
+    const int nt = std::max(1, std::min(pool.workers() + 1, (int)(Q / 128) + 1));
+    struct ThreadOut {
+        std::vector<PreparedTerm> terms;
+        uint32_t max_in_seg = 0;
+        bool unit = true, scan_always = false;
+    };
+    std::vector<std::vector<ThreadOut>> per((size_t)nt, std::vector<ThreadOut>(np));
+    parts.assign(np, DevResolved{});
+    for (size_t p = 0; p < np; p++) {
+        parts[p].qoff.assign((size_t)Q + 1, 0);  // filled with counts first, turned into offsets below
+        parts[p].weight.assign(Q, 0);
+    }
+    has.assign(Q, 0);
+    auto lo_of = [&](int t) { return (uint32_t)((uint64_t)Q * t / nt); };
+    auto work = [&](int t) {
+        std::vector<QueryTerm> qt;
+        for (size_t p = 0; p < np; p++) per[t][p].terms.reserve((size_t)(lo_of(t + 1) - lo_of(t)) * 4 * std::max<size_t>(1, g.dev_cols[p].size()));
+        for (uint32_t q = lo_of(t); q < lo_of(t + 1); q++) {
+            has[q] = terms_of(q, qt) ? 1 : 0;
+            for (size_t p = 0; p < np; p++) {
+                ThreadOut& o = per[t][p];
+                const size_t before = o.terms.size();
+                uint64_t wsum = 0;
+                const std::vector<uint32_t>& cols = g.dev_cols[p];
+                for (uint32_t slot = 0; slot < (uint32_t)cols.size(); slot++) {
+                    const uint32_t j = cols[slot];
+                    uint32_t in_seg = 0;
+                    for (const QueryTerm& x : qt) {
+                        const TermDict::Entry& en = g.dict.table[(size_t)x.gid * ncol + j];
+                        if (en.row == TermDict::kAbsent || en.count == 0) continue;  // src/api_engine.cpp:454-458
+                        o.terms.push_back(PreparedTerm{slot, en.row, en.idf, x.w, 0u, 0u});
+                        wsum += en.count;
+                        in_seg++;
+                        if (!(x.w >= 0.0f) || !(en.idf >= 0.0f)) o.scan_always = true;
+                        if (x.w != 1.0f || !(en.idf >= 9.094947017729282e-13f && en.idf <= 64.0f)) o.unit = false;
+                    }
+                    o.max_in_seg = std::max(o.max_in_seg, in_seg);
+                }
+                parts[p].qoff[q + 1] = (uint32_t)(o.terms.size() - before);
+                parts[p].weight[q] = wsum;
+            }
+        }
+    };
+    pool.run(nt, work);
+    for (size_t p = 0; p < np; p++) {
+        DevResolved& r = parts[p];
+        for (uint32_t q = 0; q < Q; q++) r.qoff[q + 1] += r.qoff[q];
+        r.terms.resize(std::max<uint32_t>(1, r.qoff[Q]));
+        size_t at = 0;
+        for (int t = 0; t < nt; t++) {
+            const ThreadOut& o = per[t][p];
+            if (!o.terms.empty()) std::memcpy(r.terms.data() + at, o.terms.data(), o.terms.size() * sizeof(PreparedTerm));
+            at += o.terms.size();
+            r.max_in_seg = std::max(r.max_in_seg, o.max_in_seg);
+            r.unit = r.unit && o.unit;
+            r.scan_always = r.scan_always || o.scan_always;
+        }
+    }
+}
+
 // start of each NUL-terminated string in a packed buffer; false if fewer than Q strings fit
 bool split_packed(const char* z, size_t nbytes, uint32_t Q, std::vector<const char*>& starts) {
     starts.resize(Q);
@@ -396,20 +473,32 @@ int search_core(ns_engine* e, const std::shared_ptr<const Generation>& gen, uint
     if (!gen) { set_error("search before a successful reload"); return NS_ERR_STATE; }
     const Generation& g = *gen;
     const size_t ndev = e->idx.size();
-    std::vector<const std::vector<uint32_t>*> colsets;
-    for (size_t d = 0; d < ndev; d++) colsets.push_back(&g.dev_cols[d]);
-    std::vector<Resolved> parts;
+    std::vector<DevResolved> parts;
     std::vector<uint8_t> has;
     using clk = std::chrono::steady_clock;
     const auto t0 = clk::now();
-    resolve_all(e, g, Q, terms_of, colsets, parts, has);
+    resolve_devices(e, g, Q, terms_of, parts, has);
     if (has_found && Q) std::memcpy(has_found, has.data(), Q);
     const auto t1 = clk::now();
     auto ms = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    // prepare on device slot d: the trusted form; if the device index carries no resident scores
+    // (NSB200_NO_RESIDENT) the same terms go through the generic, validating ns_batch_prepare
+    auto prepare = [&](size_t d, ns_batch** out) -> int {
+        const DevResolved& r = parts[d];
+        PreparedBatch pb{r.qoff.data(), r.terms.data(), r.weight.data(), r.max_in_seg, r.unit, r.scan_always};
+        int rc = batch_prepare_trusted(e->idx[d], g.dev_state[d], Q, k, pb, out);
+        if (rc != NS_ERR_STATE) return rc;
+        std::vector<uint64_t> q_off((size_t)Q + 1);
+        std::vector<ns_qterm> qt(std::max<size_t>(1, r.qoff[Q]));
+        for (uint32_t q = 0; q <= Q; q++) q_off[q] = r.qoff[q];
+        for (uint32_t i = 0; i < r.qoff[Q]; i++)
+            qt[i] = ns_qterm{g.dict.owned[g.dev_cols[d][r.terms[i].slot]], r.terms[i].row, r.terms[i].idf, r.terms[i].w};
+        return batch_prepare_on(e->idx[d], g.dev_state[d], Q, k, q_off.data(), qt.data(), out);
+    };
 
     if (ndev == 1) {
         ns_batch* b = nullptr;
-        int rc = batch_prepare_on(e->idx[0], g.dev_state[0], Q, k, parts[0].q_off.data(), parts[0].terms.data(), &b);
+        int rc = prepare(0, &b);
         if (rc != NS_OK) return rc;
         const auto t2 = clk::now();
         rc = ns_batch_launch(b, nullptr);
@@ -432,7 +521,7 @@ int search_core(ns_engine* e, const std::shared_ptr<const Generation>& gen, uint
     std::vector<int> rcs(ndev, NS_OK);
     std::vector<std::string> errs(ndev);
     auto one = [&](int d) {
-        rcs[d] = batch_prepare_on(e->idx[d], g.dev_state[d], Q, k, parts[d].q_off.data(), parts[d].terms.data(), &bs[d]);
+        rcs[d] = prepare((size_t)d, &bs[d]);
         if (rcs[d] == NS_OK) rcs[d] = ns_batch_launch_exchange(bs[d], grp->x[d], step, nullptr);
         if (rcs[d] != NS_OK) errs[d] = ns_last_error();
     };

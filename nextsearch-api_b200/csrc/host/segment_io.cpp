@@ -282,13 +282,13 @@ void TermDict::build(const std::vector<std::unique_ptr<HostSegment>>& segs) {
         }
     }
     // pass 2: the dense (term, segment) table
-    table.assign((size_t)nterms * owned.size(), Entry{kAbsent, 0.0f});
+    table.assign((size_t)nterms * owned.size(), Entry{kAbsent, 0.0f, 0u});
     for (size_t j = 0; j < owned.size(); j++) {
         const HostSegment& sg = *segs[owned[j]];
         for (size_t r = 0; r < sg.rows.size(); r++) {
             const uint32_t g = gid_of[j][r];
             if (g == kAbsent || sg.rows[r].df == 0) continue;  // shadowed duplicate row, or df == 0
-            table[(size_t)g * owned.size() + j] = Entry{(uint32_t)r, sg.rows[r].idf};
+            table[(size_t)g * owned.size() + j] = Entry{(uint32_t)r, sg.rows[r].idf, sg.rows[r].count};
         }
     }
 }

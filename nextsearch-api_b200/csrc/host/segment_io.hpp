@@ -75,6 +75,7 @@ struct TermDict {
     struct Entry {
         uint32_t row;  // kAbsent: the term is not in that segment, or its df is 0 (src/api_engine.cpp:455,458)
         float idf;     // bm25_idf(N, df) of that segment
+        uint32_t count;  // LexEntry.count: postings of the row
     };
     struct Slot {
         uint64_t h = 0;

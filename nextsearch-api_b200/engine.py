@@ -406,6 +406,23 @@ class Engine:
                                                           _ptr(found), _ptr(has)))
         return BatchResult(hits, nhits, found, has[:Q].astype(bool), K)
 
+    @staticmethod
+    def pack_queries(queries: Sequence[str]) -> bytes:
+        """The Q query strings back to back, each NUL-terminated: the host buffer ns_engine_search_batch_packed takes
+        (what a request-coalescing front end accumulates)."""
+        return ("\0".join(queries) + "\0").encode("utf-8") if len(queries) else b""
+
+    def search_batch_packed(self, zqueries: bytes, Q: int, k: int = 10) -> BatchResult:
+        """ns_engine_search_batch_packed on an already packed host buffer."""
+        K = clamp_k(k)
+        hits = np.empty((Q, K), dtype=HIT_DTYPE)
+        nhits = np.empty(Q, dtype=np.uint32)
+        found = np.empty(Q, dtype=np.uint64)
+        has = np.zeros(max(1, Q), dtype=np.uint8)
+        check(self._lib.ns_engine_search_batch_packed(self._h, Q, zqueries, len(zqueries), int(k), _ptr(hits), _ptr(nhits),
+                                                      _ptr(found), _ptr(has)))
+        return BatchResult(hits, nhits, found, has[:Q].astype(bool), K)
+
     def search_terms_batch(self, term_lists: Sequence[Sequence[Tuple[str, float]]], k: int = 10) -> BatchResult:
         """Explicit (term, qweight) lists — the reference's qterms_w — one per query (ns_engine_search_terms_batch)."""
         Q = len(term_lists)
