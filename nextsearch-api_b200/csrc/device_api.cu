@@ -122,6 +122,7 @@ struct BatchRes {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev_h2d = nullptr;  // the descriptor upload of the batch using this resource set has finished
+    cudaEvent_t ev_copy = nullptr; // result copy finished (host waits on it, sleeping)
     ~BatchRes() {
         cudaSetDevice(device);
         if (d_blob) cudaFree(d_blob);
@@ -131,6 +132,7 @@ struct BatchRes {
         for (auto& e : ev)
             if (e) cudaEventDestroy(e);
         if (ev_h2d) cudaEventDestroy(ev_h2d);
+        if (ev_copy) cudaEventDestroy(ev_copy);
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -227,6 +229,7 @@ struct ns_exchange {
     uint8_t* h_out = nullptr; // pinned, stride + 256 bytes
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_done[8] = {};  // per slot: merge of the last step using the slot has been enqueued
+    cudaEvent_t ev_copy = nullptr;  // result copy finished (host waits on it, sleeping)
     std::mutex mu;
     uint8_t* gather(uint8_t* base, uint32_t slot) const { return base + (size_t)slot * slot_bytes; }
     uint32_t* flags(uint8_t* base, uint32_t slot) const { return reinterpret_cast<uint32_t*>(base + off_flags + (size_t)slot * 256); }
@@ -713,8 +716,11 @@ int acquire_res(IndexShared* idx, size_t d_need, size_t in_need, size_t out_need
     NS_CUDA(cudaMallocHost(&r->h_in, r->h_in_cap));
     NS_CUDA(cudaMallocHost(&r->h_out, r->h_out_cap));
     NS_CUDA(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
-    for (auto& e : r->ev) NS_CUDA(cudaEventCreate(&e));
-    NS_CUDA(cudaEventCreateWithFlags(&r->ev_h2d, cudaEventDisableTiming));
+    // Blocking-sync events: a host thread that waits for the GPU sleeps instead of spinning, so that many
+    // concurrent callers (and the front-end worker threads) do not starve each other of cores.
+    for (auto& e : r->ev) NS_CUDA(cudaEventCreateWithFlags(&e, cudaEventBlockingSync));
+    NS_CUDA(cudaEventCreateWithFlags(&r->ev_h2d, cudaEventDisableTiming | cudaEventBlockingSync));
+    NS_CUDA(cudaEventCreateWithFlags(&r->ev_copy, cudaEventDisableTiming | cudaEventBlockingSync));
     out = std::move(r);
     return NS_OK;
 }
@@ -1140,7 +1146,8 @@ extern "C" int ns_batch_fetch(ns_batch* b, ns_hit* out_hits, uint32_t* out_nhits
     // order the copy after the kernels even when they ran on a caller-supplied stream
     NS_CUDA(cudaStreamWaitEvent(r.stream, r.ev[2], 0));
     NS_CUDA(cudaMemcpyAsync(r.h_out, b->d_out, b->out_bytes, cudaMemcpyDeviceToHost, r.stream));
-    NS_CUDA(cudaStreamSynchronize(r.stream));
+    NS_CUDA(cudaEventRecord(r.ev_copy, r.stream));
+    NS_CUDA(cudaEventSynchronize(r.ev_copy));
     if (out_hits) std::memcpy(out_hits, r.h_out, (size_t)b->Q * b->k * sizeof(ns_hit));
     if (out_nhits) std::memcpy(out_nhits, r.h_out + b->off_n, (size_t)b->Q * 4);
     if (out_found) std::memcpy(out_found, r.h_out + b->off_found, (size_t)b->Q * 8);
@@ -1327,6 +1334,7 @@ extern "C" int ns_exchange_create(int device, uint32_t world, uint32_t rank, uin
     if (e == cudaSuccess) e = cudaMallocHost(&x->h_out, x->stride + 256);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&x->stream, cudaStreamNonBlocking);
     for (uint32_t s = 0; e == cudaSuccess && s < slots; s++) e = cudaEventCreateWithFlags(&x->ev_done[s], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&x->ev_copy, cudaEventDisableTiming | cudaEventBlockingSync);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
         set_error(std::string("ns_exchange_create: ") + cudaGetErrorString(e));
@@ -1347,6 +1355,7 @@ extern "C" void ns_exchange_destroy(ns_exchange* x) {
     if (x->h_out) cudaFreeHost(x->h_out);
     for (auto& ev : x->ev_done)
         if (ev) cudaEventDestroy(ev);
+    if (x->ev_copy) cudaEventDestroy(x->ev_copy);
     if (x->stream) cudaStreamDestroy(x->stream);
     delete x;
 }
@@ -1475,7 +1484,8 @@ extern "C" int ns_exchange_fetch(ns_exchange* x, uint64_t step, uint32_t Q, int 
     NS_CUDA(cudaStreamWaitEvent(x->stream, x->ev_done[slot], 0));
     if (Q) NS_CUDA(cudaMemcpyAsync(x->h_out, x->merged(slot), bytes, cudaMemcpyDeviceToHost, x->stream));
     NS_CUDA(cudaMemcpyAsync(x->h_out + x->stride, x->status(slot), 4, cudaMemcpyDeviceToHost, x->stream));
-    NS_CUDA(cudaStreamSynchronize(x->stream));
+    NS_CUDA(cudaEventRecord(x->ev_copy, x->stream));
+    NS_CUDA(cudaEventSynchronize(x->ev_copy));
     uint32_t st = 0;
     std::memcpy(&st, x->h_out + x->stride, 4);
     if (st != 0) {

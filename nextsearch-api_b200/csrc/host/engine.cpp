@@ -96,6 +96,8 @@ struct ns_engine {
     std::once_flag pool_once;
     std::mutex xg_mu;
     std::vector<std::unique_ptr<XGroup>> xg_pool;
+    std::mutex sc_mu;
+    std::vector<std::shared_ptr<void>> sc_pool;  // ResolveScratch objects (type-erased: defined further down)
     std::unique_ptr<Coalescer> coalescer;
     std::mutex co_mu;               // guards `coalescer` start/stop
     ReloadStats last_reload;
@@ -253,10 +255,20 @@ bool query_terms_of(const Generation& g, const char* query, std::vector<QueryTer
     query_term_spans(query, buf, spans);
     if (spans.empty() || g.seg_names.empty()) return false;
     if (!g.sem.enabled) {
-        for (const TokSpan& s : spans) {
-            const char* p = buf.data() + s.off;
-            const int64_t gid = g.dict.find(p, s.len, term_hash(p, s.len));
-            if (gid >= 0) out.push_back(QueryTerm{(uint32_t)gid, 1.0f});
+        // hash every token and ask for its dictionary slot first, probe afterwards: the cache misses of one
+        // query's tokens overlap instead of following each other
+        static thread_local std::vector<uint64_t> hashes;
+        hashes.resize(spans.size());
+        for (size_t i = 0; i < spans.size(); i++) {
+            hashes[i] = term_hash(buf.data() + spans[i].off, spans[i].len);
+            g.dict.prefetch(hashes[i]);
+        }
+        const size_t ncol = g.dict.owned.size();
+        for (size_t i = 0; i < spans.size(); i++) {
+            const int64_t gid = g.dict.find(buf.data() + spans[i].off, spans[i].len, hashes[i]);
+            if (gid < 0) continue;
+            __builtin_prefetch(g.dict.table.data() + (size_t)gid * ncol);
+            out.push_back(QueryTerm{(uint32_t)gid, 1.0f});
         }
         return true;
     }
@@ -348,23 +360,47 @@ struct DevResolved {
     bool unit = true, scan_always = false;
 };
 
-template <class TermsOf>
-void resolve_devices(ns_engine* e, const Generation& g, uint32_t Q, TermsOf terms_of, std::vector<DevResolved>& parts,
-                     std::vector<uint8_t>& has) {
-    const size_t np = g.dev_cols.size();
-    const size_t ncol = g.dict.owned.size();
-    WorkPool& pool = e->workers();
-    const int nt = std::max(1, std::min(pool.workers() + 1, (int)(Q / 128) + 1));
+// Buffers of one front-end pass, pooled by the engine: their capacity survives from call to call.  (Fresh
+// megabyte-sized vectors per call are mmap'ed and unmapped by malloc every time, which serialises concurrent
+// callers on the process's address-space lock.)
+struct ResolveScratch {
     struct ThreadOut {
         std::vector<PreparedTerm> terms;
         uint32_t max_in_seg = 0;
         bool unit = true, scan_always = false;
     };
-    std::vector<std::vector<ThreadOut>> per((size_t)nt, std::vector<ThreadOut>(np));
-    parts.assign(np, DevResolved{});
+    std::vector<DevResolved> parts;
+    std::vector<std::vector<ThreadOut>> per;
+    std::vector<uint8_t> has;
+};
+
+template <class TermsOf>
+void resolve_devices(ns_engine* e, const Generation& g, uint32_t Q, TermsOf terms_of, ResolveScratch& sc) {
+    using ThreadOut = ResolveScratch::ThreadOut;
+    std::vector<DevResolved>& parts = sc.parts;
+    std::vector<uint8_t>& has = sc.has;
+    const size_t np = g.dev_cols.size();
+    const size_t ncol = g.dict.owned.size();
+    WorkPool& pool = e->workers();
+    const int nt = std::max(1, std::min(pool.workers() + 1, (int)(Q / 128) + 1));
+    std::vector<std::vector<ThreadOut>>& per = sc.per;
+    if (per.size() < (size_t)nt) per.resize((size_t)nt);
+    for (int t = 0; t < nt; t++) {
+        per[t].resize(np);
+        for (auto& o : per[t]) {
+            o.terms.clear();
+            o.max_in_seg = 0;
+            o.unit = true;
+            o.scan_always = false;
+        }
+    }
+    parts.resize(np);
     for (size_t p = 0; p < np; p++) {
         parts[p].qoff.assign((size_t)Q + 1, 0);  // filled with counts first, turned into offsets below
         parts[p].weight.assign(Q, 0);
+        parts[p].max_in_seg = 0;
+        parts[p].unit = true;
+        parts[p].scan_always = false;
     }
     has.assign(Q, 0);
     auto lo_of = [&](int t) { return (uint32_t)((uint64_t)Q * t / nt); };
@@ -473,11 +509,28 @@ int search_core(ns_engine* e, const std::shared_ptr<const Generation>& gen, uint
     if (!gen) { set_error("search before a successful reload"); return NS_ERR_STATE; }
     const Generation& g = *gen;
     const size_t ndev = e->idx.size();
-    std::vector<DevResolved> parts;
-    std::vector<uint8_t> has;
+    std::shared_ptr<ResolveScratch> scratch;
+    {
+        std::lock_guard<std::mutex> lk(e->sc_mu);
+        if (!e->sc_pool.empty()) {
+            scratch = std::static_pointer_cast<ResolveScratch>(e->sc_pool.back());
+            e->sc_pool.pop_back();
+        }
+    }
+    if (!scratch) scratch = std::make_shared<ResolveScratch>();
+    struct GiveBack {
+        ns_engine* e;
+        std::shared_ptr<ResolveScratch>& s;
+        ~GiveBack() {
+            std::lock_guard<std::mutex> lk(e->sc_mu);
+            if (e->sc_pool.size() < 32) e->sc_pool.push_back(std::static_pointer_cast<void>(s));
+        }
+    } give_back{e, scratch};
+    std::vector<DevResolved>& parts = scratch->parts;
+    std::vector<uint8_t>& has = scratch->has;
     using clk = std::chrono::steady_clock;
     const auto t0 = clk::now();
-    resolve_devices(e, g, Q, terms_of, parts, has);
+    resolve_devices(e, g, Q, terms_of, *scratch);
     if (has_found && Q) std::memcpy(has_found, has.data(), Q);
     const auto t1 = clk::now();
     auto ms = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };

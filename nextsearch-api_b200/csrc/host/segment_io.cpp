@@ -270,13 +270,17 @@ void TermDict::build(const std::vector<std::unique_ptr<HostSegment>>& segs) {
                 Slot& sl = slots[i];
                 if (sl.gid == kAbsent) {
                     sl.h = h;
-                    sl.key_off = (uint32_t)keys.size();
                     sl.key_len = (uint32_t)term.size();
                     sl.gid = nterms++;
-                    keys.insert(keys.end(), term.begin(), term.end());
+                    if (term.size() <= sizeof(sl.inl)) {
+                        std::memcpy(sl.inl, term.data(), term.size());
+                    } else {
+                        sl.key_off = (uint32_t)keys.size();
+                        keys.insert(keys.end(), term.begin(), term.end());
+                    }
                     break;
                 }
-                if (sl.h == h && sl.key_len == term.size() && std::memcmp(keys.data() + sl.key_off, term.data(), term.size()) == 0) break;
+                if (sl.h == h && key_equal(sl, keys.data(), term.data(), term.size())) break;
             }
             gid_of[j][kv.second] = slots[i].gid;
         }

@@ -77,11 +77,12 @@ struct TermDict {
         float idf;     // bm25_idf(N, df) of that segment
         uint32_t count;  // LexEntry.count: postings of the row
     };
-    struct Slot {
+    struct Slot {  // 32 bytes: a probe touches one cache line, keys of up to 12 bytes are compared in place
         uint64_t h = 0;
-        uint32_t key_off = 0, key_len = 0;
         uint32_t gid = kAbsent;  // kAbsent = empty slot
-        uint32_t pad = 0;
+        uint32_t key_off = 0;    // into keys[] (longer keys)
+        uint32_t key_len = 0;
+        char inl[12] = {0};
     };
     std::vector<uint32_t> owned;   // global segment index of column j, ascending
     std::vector<Slot> slots;
@@ -92,13 +93,20 @@ struct TermDict {
 
     // segs[i] may be null (not owned)
     void build(const std::vector<std::unique_ptr<HostSegment>>& segs);
+    static bool key_equal(const Slot& s, const char* keys, const char* p, size_t n) {
+        if (s.key_len != n) return false;
+        return std::memcmp(n <= sizeof(s.inl) ? s.inl : keys + s.key_off, p, n) == 0;
+    }
+    void prefetch(uint64_t h) const {
+        if (!slots.empty()) __builtin_prefetch(&slots[(size_t)(h & mask)]);
+    }
     // global term id or -1
     int64_t find(const char* p, size_t n, uint64_t h) const {
         if (slots.empty()) return -1;
         for (size_t i = (size_t)(h & mask);; i = (i + 1) & mask) {
             const Slot& s = slots[i];
             if (s.gid == kAbsent) return -1;
-            if (s.h == h && s.key_len == n && std::memcmp(keys.data() + s.key_off, p, n) == 0) return (int64_t)s.gid;
+            if (s.h == h && key_equal(s, keys.data(), p, n)) return (int64_t)s.gid;
         }
     }
     const Entry* row_of(uint32_t gid) const { return table.data() + (size_t)gid * owned.size(); }
