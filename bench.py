@@ -326,35 +326,70 @@ def device_workload(torch, eng, batches, k, stream, W, K):
     return out
 
 
-def run_callers(call, n_calls, callers):
-    """n_calls invocations of call(i) issued by `callers` host threads.  Returns (seconds, last result)."""
-    last_box = [None]
-    if callers <= 1:
+class Callers:
+    """`callers` persistent host threads issuing calls.  The threads outlive one run: a thread's first CUDA call on
+    every device of a multi-GPU engine binds it to that device's context, which belongs to warm-up, not to the
+    timed region."""
+
+    def __init__(self, callers: int):
+        from concurrent.futures import ThreadPoolExecutor
+
+        self.n = max(1, callers)
+        self.pool = ThreadPoolExecutor(max_workers=self.n) if self.n > 1 else None
+
+    def run(self, call, n_calls):
+        """n_calls invocations of call(i).  Returns (seconds, result of the last call)."""
+        if self.pool is None:
+            t0 = time.perf_counter()
+            last = None
+            for i in range(n_calls):
+                last = call(i)
+            return time.perf_counter() - t0, last
+        nxt = [0]
+        lock = threading.Lock()
+        last_box = [None]
+
+        def worker():
+            while True:
+                with lock:
+                    i = nxt[0]
+                    nxt[0] += 1
+                if i >= n_calls:
+                    return
+                r = call(i)
+                if i == n_calls - 1:
+                    last_box[0] = r
+
         t0 = time.perf_counter()
-        for i in range(n_calls):
-            last_box[0] = call(i)
+        futs = [self.pool.submit(worker) for _ in range(self.n)]
+        for f in futs:
+            f.result()
         return time.perf_counter() - t0, last_box[0]
-    nxt = [0]
-    lock = threading.Lock()
 
-    def worker():
-        while True:
-            with lock:
-                i = nxt[0]
-                nxt[0] += 1
-            if i >= n_calls:
-                return
-            r = call(i)
-            if i == n_calls - 1:
-                last_box[0] = r
+    def close(self):
+        if self.pool is not None:
+            self.pool.shutdown()
 
-    ths = [threading.Thread(target=worker) for _ in range(callers)]
-    t0 = time.perf_counter()
-    for t in ths:
-        t.start()
-    for t in ths:
-        t.join()
-    return time.perf_counter() - t0, last_box[0]
+
+def run_callers(call, n_calls, callers):
+    c = Callers(callers)
+    try:
+        return c.run(call, n_calls)
+    finally:
+        c.close()
+
+
+def measure_e2e(call, e2e_steps, callers):
+    """single-caller and `callers`-thread throughput of call(i); returns (single_s, multi_s, multi_calls, last)."""
+    for i in range(2):
+        call(i)
+    single_s, last = run_callers(call, e2e_steps, 1)
+    team = Callers(callers)
+    n = e2e_steps * max(1, callers // 2)
+    team.run(call, 2 * callers)      # every thread has touched every device; pooled buffers exist
+    multi_s, last2 = team.run(call, n)
+    team.close()
+    return single_s, multi_s, n, (last2 if last2 is not None else last)
 
 
 def oracle_parity(path, queries, result, k, nchk=256):
@@ -467,7 +502,7 @@ def ours(args, rank, world, local_rank):
         b.batch.close()
 
     # ---- e2e through the C ABI with host buffers ----
-    e2e_steps = max(3, min(K, args.e2e_steps)) * (2 if world > 1 else 1)
+    e2e_steps = max(3, min(K, args.e2e_steps))
     parity = None
     e2e = {"unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h, "steps": e2e_steps}
     # host input of one e2e call: the batch's query strings as ONE packed byte buffer (NUL-separated), the form
@@ -477,18 +512,14 @@ def ours(args, rank, world, local_rank):
     if world == 1:
         def call(i):
             return eng.search_batch_packed(packed[i % nb], BATCH_Q, TOPK)
-        for i in range(2):
-            call(i)
-        single_s, last = run_callers(call, e2e_steps, 1)
         callers = max(1, args.e2e_callers)
-        run_callers(call, e2e_steps, callers)  # warm the extra callers' pooled buffers
-        e2e_s, last = run_callers(call, e2e_steps, callers)
-        e2e.update({"value": e2e_steps * BATCH_Q / e2e_s, "callers": callers,
+        single_s, e2e_s, n_multi, last = measure_e2e(call, e2e_steps, callers)
+        e2e.update({"value": n_multi * BATCH_Q / e2e_s, "callers": callers, "calls": n_multi,
                     "single_caller_value": e2e_steps * BATCH_Q / single_s,
                     "path": "ns_engine_search_batch_packed(query strings): tokenise, lexicon, prepare, H2D, kernels, D2H per "
                             "call; `callers` host threads issue the calls"})
         extra["p50_ms_batch_e2e"] = 1e3 * single_s / e2e_steps
-        last_idx = (e2e_steps - 1) % nb
+        last_idx = (n_multi - 1) % nb
         multi = eng
     else:
         # (a) one process per GPU: every rank runs the pipeline (host front end of batch i+1 under the GPUs' batch i)
@@ -523,19 +554,15 @@ def ours(args, rank, world, local_rank):
 
             def call(i):
                 return multi.search_batch_packed(packed[i % nb], BATCH_Q, TOPK)
-            for i in range(2):
-                call(i)
-            single_s, last = run_callers(call, e2e_steps, 1)
-            callers = max(1, args.e2e_callers, min(2 * world, (os.cpu_count() or 8) // 2))
-            run_callers(call, e2e_steps, callers)
-            e2e_s, last = run_callers(call, e2e_steps, callers)
-            e2e.update({"value": e2e_steps * BATCH_Q / e2e_s, "callers": callers,
+            callers = max(1, args.e2e_callers, min(2 * world + 4, (os.cpu_count() or 8) // 2))
+            single_s, e2e_s, n_multi, last = measure_e2e(call, e2e_steps, callers)
+            e2e.update({"value": n_multi * BATCH_Q / e2e_s, "callers": callers, "calls": n_multi,
                         "single_caller_value": e2e_steps * BATCH_Q / single_s,
                         "path": "ns_engine_search_batch_packed on ONE engine handle spanning the N GPUs (ns_engine_create_multi, "
                                 "rank 0's process): tokenise + lexicon ONCE per batch, per-GPU prepare + H2D, score kernels "
                                 "publish into GPU 0's gather buffer (peer memory), merge, one D2H; `callers` host threads"})
             extra["p50_ms_batch_e2e"] = 1e3 * single_s / e2e_steps
-            last_idx = (e2e_steps - 1) % nb
+            last_idx = (n_multi - 1) % nb
             same = (np.array_equal(per_rank_last.nhits, last.nhits) and np.array_equal(per_rank_last.found, last.found))
             extra["per_rank_equals_single_process"] = bool(same)
 
@@ -566,8 +593,10 @@ def ours(args, rank, world, local_rank):
             e2e["coalesced_by_callers"] = sweep
             multi.coalescer_stop()
             # the same single-request traffic WITHOUT the coalescer (every caller launches its own Q=1 batch)
-            r = multi.load_test(batches[2 % nb], 64, 64, TOPK)
-            e2e["uncoalesced_64_callers"] = {"qps": r["qps"], "p50_ms": r["p50_us"] / 1e3, "p99_ms": r["p99_us"] / 1e3}
+            multi.load_test(batches[2 % nb], 16, 32, TOPK)
+            r = multi.load_test(batches[2 % nb], 16, 512, TOPK)
+            e2e["uncoalesced_16_callers"] = {"qps": r["qps"], "p50_ms": r["p50_us"] / 1e3, "p99_ms": r["p99_us"] / 1e3,
+                                             "note": "p99 includes each fresh caller thread's first CUDA call on every device"}
         except Exception as ex:  # noqa: BLE001
             e2e["coalesced_error"] = repr(ex)[:200]
 
@@ -740,7 +769,9 @@ def single_process_multi_gpu(args):
 
     n = args.gpus
     path = ensure_index(SEGS_SHARDED)
-    eng = nsb200.Engine(path, devices=list(range(n)))
+    devices = [int(x) for x in args.devices.split(",")] if args.devices else list(range(n))
+    n = len(devices)
+    eng = nsb200.Engine(path, devices=devices)
     assert eng.reload(), eng.last_error
     nb = args.distinct_batches
     batches = make_batches(nb)
@@ -749,17 +780,13 @@ def single_process_multi_gpu(args):
 
     def call(i):
         return eng.search_batch_packed(packed[i % nb], BATCH_Q, TOPK)
-    for i in range(3):
-        call(i)
-    steps = max(3, args.e2e_steps) * 2
-    single_s, last = run_callers(call, steps, 1)
-    args.e2e_callers = max(args.e2e_callers, min(2 * n, (os.cpu_count() or 8) // 2))
-    run_callers(call, steps, args.e2e_callers)
-    e2e_s, last = run_callers(call, steps, args.e2e_callers)
+    steps = max(3, args.e2e_steps)
+    callers = max(args.e2e_callers, min(2 * n, (os.cpu_count() or 8) // 2))
+    single_s, e2e_s, n_multi, last = measure_e2e(call, steps, callers)
     line = {"metric": METRIC, "single_process": True, "n_gpus": n, "unit": UNIT,
-            "e2e": {"value": steps * BATCH_Q / e2e_s, "single_caller_value": steps * BATCH_Q / single_s, "callers": args.e2e_callers,
-                    "steps": steps},
-            "parity_sample": oracle_parity(path, batches[(steps - 1) % nb], last, TOPK), "config": workload_config(n, SEGS_SHARDED)}
+            "e2e": {"value": n_multi * BATCH_Q / e2e_s, "single_caller_value": steps * BATCH_Q / single_s, "callers": callers,
+                    "calls": n_multi},
+            "parity_sample": oracle_parity(path, batches[(n_multi - 1) % nb], last, TOPK), "config": workload_config(n, SEGS_SHARDED)}
     print(json.dumps(line), flush=True)
     eng.close()
 
@@ -784,6 +811,7 @@ def main():
     ap.add_argument("--configs4", action="store_true", default=os.environ.get("NSB200_BENCH_CONFIGS4", "1") != "0",
                     help="N=8: also run BASELINE configs[4] (8M docs in 64 segments) as an extra key")
     ap.add_argument("--single-process", action="store_true", help="N GPUs from one process through one engine handle")
+    ap.add_argument("--devices", default="", help="--single-process: explicit device slots, e.g. 0,1,0,1 (a GPU may repeat)")
     ap.add_argument("--profile-mode", action="store_true",
                     help="kernels only (for ncu): skip e2e, single-query latency and the CPU baseline leg")
     ap.add_argument("--ref-replicas", type=int, default=0)

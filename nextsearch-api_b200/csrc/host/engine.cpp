@@ -20,6 +20,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <deque>
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -79,12 +80,77 @@ struct XGroup {
 
 struct Coalescer;
 
+// One host thread per device slot of a multi-device engine; every CUDA call that touches device d outside
+// device 0 — prepare, launch, batch teardown — runs on thread d.  A host thread's first CUDA call on a device
+// binds it to that device's context, which costs milliseconds; with caller threads (or pool workers) fanning
+// out to all devices themselves that price is paid once per (thread, device) PAIR and keeps recurring as new
+// threads appear.  With device threads it is paid ndev times, at start-up.
+class DeviceWorker {
+  public:
+    DeviceWorker() : th_([this] { loop(); }) {}
+    ~DeviceWorker() {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        th_.join();
+    }
+    void submit(std::function<void()> fn) {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            q_.push_back(std::move(fn));
+        }
+        cv_.notify_one();
+    }
+
+  private:
+    void loop() {
+        for (;;) {
+            std::function<void()> fn;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return stop_ || !q_.empty(); });
+                if (q_.empty()) return;  // stop requested and nothing left
+                fn = std::move(q_.front());
+                q_.pop_front();
+            }
+            fn();
+        }
+    }
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::deque<std::function<void()>> q_;
+    bool stop_ = false;
+    std::thread th_;
+};
+
+// counts down to zero; wait() returns then
+class Latch {
+  public:
+    explicit Latch(int n) : n_(n) {}
+    void done() {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (--n_ == 0) cv_.notify_all();
+    }
+    void wait() {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return n_ == 0; });
+    }
+
+  private:
+    std::mutex mu_;
+    std::condition_variable cv_;
+    int n_;
+};
+
 }  // namespace
 
 struct ns_engine {
     std::string index_dir;
     std::vector<int> devices;       // CUDA ordinals, empty = host-only engine
     std::vector<ns_index*> idx;     // one per device slot
+    std::vector<std::unique_ptr<DeviceWorker>> dev_threads;  // multi-device engines: one per device slot
     int rank = 0, world = 1;        // process-level share: segment i is owned when i % world == rank
     bool trace = false;             // NSB200_TRACE (read at create): per-phase host timings of every search on stderr
     bool keep_raw = false;          // NSB200_KEEP_RAW (read at create): keep {docId, tf} next to the resident scores, so that
@@ -499,7 +565,7 @@ int acquire_group(ns_engine* e, uint32_t Q, std::unique_ptr<XGroup>& out) {
 
 void release_group(ns_engine* e, std::unique_ptr<XGroup> g) {
     std::lock_guard<std::mutex> lk(e->xg_mu);
-    if (e->xg_pool.size() < 16) e->xg_pool.push_back(std::move(g));
+    if (e->xg_pool.size() < 64) e->xg_pool.push_back(std::move(g));
 }
 
 template <class TermsOf>
@@ -573,12 +639,25 @@ int search_core(ns_engine* e, const std::shared_ptr<const Generation>& gen, uint
     std::vector<ns_batch*> bs(ndev, nullptr);
     std::vector<int> rcs(ndev, NS_OK);
     std::vector<std::string> errs(ndev);
+    std::vector<double> t_prep(ndev, 0.0), t_launch(ndev, 0.0);
     auto one = [&](int d) {
+        const auto a = clk::now();
         rcs[d] = prepare((size_t)d, &bs[d]);
+        const auto b = clk::now();
         if (rcs[d] == NS_OK) rcs[d] = ns_batch_launch_exchange(bs[d], grp->x[d], step, nullptr);
         if (rcs[d] != NS_OK) errs[d] = ns_last_error();
+        t_prep[d] = ms(a, b);
+        t_launch[d] = ms(b, clk::now());
     };
-    e->workers().run((int)ndev, one);
+    {
+        Latch latch((int)ndev);
+        for (size_t d = 0; d < ndev; d++)
+            e->dev_threads[d]->submit([&, d] {
+                one((int)d);
+                latch.done();
+            });
+        latch.wait();
+    }
     const auto t2 = clk::now();
     for (size_t d = 0; d < ndev && rc == NS_OK; d++)
         if (rcs[d] != NS_OK) {
@@ -586,14 +665,29 @@ int search_core(ns_engine* e, const std::shared_ptr<const Generation>& gen, uint
             set_error(errs[d]);
         }
     if (rc == NS_OK) rc = exchange_root_merge(grp->x[0], bs.data(), (int)ndev, step, Q, k);
+    const auto t2b = clk::now();
     if (rc == NS_OK) rc = ns_exchange_fetch(grp->x[0], step, Q, k, out_hits, out_nhits, out_found);
     const auto t3 = clk::now();
     std::string keep = rc != NS_OK ? std::string(ns_last_error()) : std::string();
-    for (auto* b : bs)
-        if (b) ns_batch_destroy(b);  // waits for that device's kernels
+    // Teardown (waits for that device's kernels, returns the buffers to the device's pool) on the device threads;
+    // nothing below depends on it.  The batches hold their generation's device state alive until then.
+    for (size_t d = 0; d < ndev; d++)
+        if (bs[d]) {
+            ns_batch* b = bs[d];
+            e->dev_threads[d]->submit([b] { ns_batch_destroy(b); });
+        }
     if (e->trace)
-        std::fprintf(stderr, "[nsb200] Q=%u ndev=%zu resolve %.3f ms, prepare+launch %.3f, merge+fetch %.3f, destroy %.3f\n", Q, ndev,
-                     ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, clk::now()));
+    {
+        double sp = 0, sl = 0;
+        for (size_t d = 0; d < ndev; d++) {
+            sp += t_prep[d];
+            sl += t_launch[d];
+        }
+        std::fprintf(stderr,
+                     "[nsb200] Q=%u ndev=%zu resolve %.3f ms, prepare+launch %.3f (sum over devices: prepare %.3f, launch %.3f), "
+                     "root merge enqueue %.3f, fetch(wait) %.3f, destroy %.3f\n",
+                     Q, ndev, ms(t0, t1), ms(t1, t2), sp, sl, ms(t2, t2b), ms(t2b, t3), ms(t3, clk::now()));
+    }
     if (rc == NS_OK) release_group(e, std::move(grp));  // a failed group is dropped: its flags may be in any state
     else set_error(keep);
     return rc;
@@ -773,6 +867,8 @@ extern "C" int ns_engine_create_multi(const char* index_dir, int ndev, const int
         e->idx.push_back(ix);
         e->devices.push_back(devices[d]);
     }
+    if (ndev > 1)
+        for (int d = 0; d < ndev; d++) e->dev_threads.emplace_back(new DeviceWorker());
     *out = e.release();
     return NS_OK;
 fail_cuda:
@@ -791,6 +887,7 @@ extern "C" void ns_engine_destroy(ns_engine* e) {
         std::lock_guard<std::mutex> lk(e->co_mu);
         e->coalescer.reset();  // drains and joins the dispatchers
     }
+    e->dev_threads.clear();  // runs what is queued (batch teardowns), then joins
     e->xg_pool.clear();
     {
         std::lock_guard<std::mutex> lk(e->gen_mu);
