@@ -386,7 +386,8 @@ def measure_e2e(call, e2e_steps, callers):
     single_s, last = run_callers(call, e2e_steps, 1)
     team = Callers(callers)
     n = e2e_steps * max(1, callers // 2)
-    team.run(call, 2 * callers)      # every thread has touched every device; pooled buffers exist
+    team.run(call, 8 * callers)      # warm-up at full concurrency: the engine's pooled per-call resources (pinned staging,
+                                     # device blobs, exchange groups) are allocated on first use and reused afterwards
     multi_s, last2 = team.run(call, n)
     team.close()
     return single_s, multi_s, n, (last2 if last2 is not None else last)

@@ -225,6 +225,7 @@ struct ns_exchange {
     };
     std::vector<Dest> dests;
     bool receiver = false;    // this rank is one of its own destinations: it waits for all ranks and merges
+    bool publisher_only = false;  // created without gather / merged / pinned buffers (cannot receive, cannot be a destination)
     uint64_t timeout_ns = 10000000000ull;  // NSB200_EXCHANGE_TIMEOUT_MS, default 10 s
     uint8_t* h_out = nullptr; // pinned, stride + 256 bytes
     cudaStream_t stream = nullptr;
@@ -832,6 +833,10 @@ int finish_prepare(ns_index* idx, const std::shared_ptr<IndexState>& st, std::un
     const size_t sz_terms = align_up(std::max<size_t>(1, nkept) * sizeof(DevTerm));
     const size_t sz_dist = align_up(std::max<size_t>(1, dist.size()) * sizeof(DevDistinct));
     const size_t sz_dstart = align_up(dstart.size() * 4);
+    // Room for an explicit item list (ns_batch_set_splits, query-major mode) is only reserved while it is small;
+    // large batches run with implicit items (order[] only) and keep their pinned / device blobs small.
+    const bool explicit_mode = idx->sh->tun.explicit_items || idx->sh->tun.window_tiles == 0;
+    if (!explicit_mode && b->items_cap * sizeof(DevItem) > (1u << 20)) b->items_cap = ((size_t)Q + 1) / 2;  // = Q * 4 bytes of order[]
     const size_t sz_items = align_up(std::max<size_t>(1, b->items_cap) * sizeof(DevItem));
     const size_t off_dist = sz_qoff + sz_terms;
     const size_t off_dstart = off_dist + sz_dist;
@@ -1036,6 +1041,15 @@ extern "C" int ns_batch_set_splits(ns_batch* b, uint32_t splits) {
     if (!b) return NS_ERR_INVALID;
     NS_CUDA(cudaSetDevice(b->st->device));
     if (b->launched) NS_CUDA(cudaEventSynchronize(b->res->ev[2]));
+    {
+        const size_t tiles = std::max<uint32_t>(1, b->st->total_tiles);
+        const size_t need = (size_t)b->Q * std::min<size_t>(std::min<size_t>(splits ? splits : kMaxSplit, tiles), kMaxSplit);
+        if (need > b->items_cap) {
+            set_error("ns_batch_set_splits: this batch was prepared without room for an explicit item list (large batch); "
+                      "set NSB200_EXPLICIT_ITEMS=1 before creating the index");
+            return NS_ERR_STATE;
+        }
+    }
     const size_t items_bytes = build_items(b, std::min<uint32_t>(splits, kMaxSplit));
     BatchRes& r = *b->res;
     NS_CUDA(cudaMemcpyAsync(r.d_blob + b->off_items, r.h_in + b->off_items, items_bytes, cudaMemcpyHostToDevice, r.stream));
@@ -1295,8 +1309,9 @@ int upload_pub(ns_exchange* x) {
         p.src = x->rank;
         p.stride = x->stride;
         for (size_t d = 0; d < x->dests.size(); d++) {
-            p.blob[d] = x->gather(x->dests[d].base, s);
-            p.flag[d] = x->flags(x->dests[d].base, s);
+            // addresses inside the DESTINATION's memory: always the full (receiver) layout, whatever this rank's own is
+            p.blob[d] = x->dests[d].base + (size_t)s * x->slot_bytes;
+            p.flag[d] = reinterpret_cast<uint32_t*>(x->dests[d].base + (size_t)x->slots * x->slot_bytes + (size_t)s * 256);
         }
     }
     NS_CUDA(cudaSetDevice(x->device));
@@ -1306,8 +1321,21 @@ int upload_pub(ns_exchange* x) {
 
 }  // namespace
 
+static int exchange_create_impl(int device, uint32_t world, uint32_t rank, uint32_t max_queries, uint32_t slots,
+                                bool publisher_only, ns_exchange** out);
+
 extern "C" int ns_exchange_create(int device, uint32_t world, uint32_t rank, uint32_t max_queries, uint32_t slots,
                                   ns_exchange** out) {
+    return exchange_create_impl(device, world, rank, max_queries, slots, false, out);
+}
+
+int nsb::exchange_create_publisher(int device, uint32_t world, uint32_t rank, uint32_t max_queries, uint32_t slots,
+                                   ns_exchange** out) {
+    return exchange_create_impl(device, world, rank, max_queries, slots, true, out);
+}
+
+static int exchange_create_impl(int device, uint32_t world, uint32_t rank, uint32_t max_queries, uint32_t slots,
+                                bool publisher_only, ns_exchange** out) {
     if (!out || world == 0 || world > NS_MAX_PEERS || rank >= world || slots == 0 || slots > 8 || max_queries == 0) {
         set_error("ns_exchange_create: bad argument (world <= NS_MAX_PEERS, rank < world, 1 <= slots <= 8)");
         return NS_ERR_INVALID;
@@ -1322,16 +1350,26 @@ extern "C" int ns_exchange_create(int device, uint32_t world, uint32_t rank, uin
     x->max_q = max_queries;
     x->stride = blob_capacity(max_queries);
     x->slot_bytes = (size_t)world * x->stride;
-    x->off_flags = (size_t)slots * x->slot_bytes;
-    x->off_status = x->off_flags + (size_t)slots * 256;
-    x->off_merged = x->off_status + (size_t)slots * 256;
-    x->off_pub = x->off_merged + (size_t)slots * x->stride;
+    x->publisher_only = publisher_only;
+    if (publisher_only) {
+        // a rank that only publishes needs neither gather regions nor a merged blob nor a pinned result buffer:
+        // its device memory holds the flags / status words (unused) and the PublishDest table
+        x->off_flags = 0;
+        x->off_status = (size_t)slots * 256;
+        x->off_merged = x->off_status + (size_t)slots * 256;
+        x->off_pub = x->off_merged;
+    } else {
+        x->off_flags = (size_t)slots * x->slot_bytes;
+        x->off_status = x->off_flags + (size_t)slots * 256;
+        x->off_merged = x->off_status + (size_t)slots * 256;
+        x->off_pub = x->off_merged + (size_t)slots * x->stride;
+    }
     x->total = x->off_pub + align_up((size_t)slots * sizeof(PublishDest));
     if (const char* s = std::getenv("NSB200_EXCHANGE_TIMEOUT_MS")) x->timeout_ns = (uint64_t)std::max(1L, std::atol(s)) * 1000000ull;
     cudaError_t e = cudaMalloc(&x->d_mem, x->total);
     // flags and status start at 0; epochs start at 1
     if (e == cudaSuccess) e = cudaMemset(x->d_mem + x->off_flags, 0, x->off_merged - x->off_flags);
-    if (e == cudaSuccess) e = cudaMallocHost(&x->h_out, x->stride + 256);
+    if (e == cudaSuccess && !publisher_only) e = cudaMallocHost(&x->h_out, x->stride + 256);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&x->stream, cudaStreamNonBlocking);
     for (uint32_t s = 0; e == cudaSuccess && s < slots; s++) e = cudaEventCreateWithFlags(&x->ev_done[s], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&x->ev_copy, cudaEventDisableTiming | cudaEventBlockingSync);
@@ -1361,7 +1399,7 @@ extern "C" void ns_exchange_destroy(ns_exchange* x) {
 }
 
 extern "C" int ns_exchange_ipc_handle(ns_exchange* x, void* handle) {
-    if (!x || !handle) { set_error("ns_exchange_ipc_handle: null"); return NS_ERR_INVALID; }
+    if (!x || !handle || x->publisher_only) { set_error("ns_exchange_ipc_handle: null or publisher-only exchange"); return NS_ERR_INVALID; }
     static_assert(sizeof(cudaIpcMemHandle_t) == NS_IPC_HANDLE_BYTES, "handle size");
     NS_CUDA(cudaSetDevice(x->device));
     cudaIpcMemHandle_t h;
@@ -1392,6 +1430,7 @@ extern "C" int ns_exchange_attach_ipc(ns_exchange* x, uint32_t peer_rank, const 
 
 extern "C" int ns_exchange_attach_local(ns_exchange* x, ns_exchange* peer) {
     if (!x || !peer) { set_error("ns_exchange_attach_local: null"); return NS_ERR_INVALID; }
+    if (peer->publisher_only) { set_error("ns_exchange_attach_local: the destination was created as a publisher only"); return NS_ERR_INVALID; }
     if (peer->world != x->world || peer->stride != x->stride || peer->slots != x->slots) {
         set_error("ns_exchange_attach_local: the two exchanges were created with different shapes");
         return NS_ERR_INVALID;

@@ -41,6 +41,11 @@ struct PreparedBatch {
 int batch_prepare_trusted(ns_index* idx, const std::shared_ptr<const void>& state, uint32_t Q, int k, const PreparedBatch& pb,
                           ns_batch** out);
 
+// An exchange that only publishes (the non-root device slots of a multi-device engine): no gather regions, no
+// merged blob, no pinned result buffer — creating it costs one small device allocation.
+int exchange_create_publisher(int device, uint32_t world, uint32_t rank, uint32_t max_queries, uint32_t slots,
+                              ns_exchange** out);
+
 // Multi-device engine, root side of one step: order the root batch's stream after the score kernels of every
 // other device's batch (events — same process, so nothing has to poll) and enqueue the merge of the `ndev`
 // blobs the score kernels stored into the root's gather buffer.  batches[0] is the root's.

@@ -552,7 +552,8 @@ int acquire_group(ns_engine* e, uint32_t Q, std::unique_ptr<XGroup>& out) {
     const uint32_t ndev = (uint32_t)e->devices.size();
     g->x.assign(ndev, nullptr);
     for (uint32_t d = 0; d < ndev; d++) {
-        int rc = ns_exchange_create(e->devices[d], ndev, d, cap, 1, &g->x[d]);
+        int rc = d == 0 ? ns_exchange_create(e->devices[d], ndev, d, cap, 1, &g->x[d])
+                        : exchange_create_publisher(e->devices[d], ndev, d, cap, 1, &g->x[d]);
         if (rc != NS_OK) return rc;
     }
     for (uint32_t d = 0; d < ndev; d++) {  // everybody publishes into the root's gather buffer; the root receives

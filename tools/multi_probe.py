@@ -14,7 +14,7 @@ def call(i): return e.search_batch_packed(z[i % 4], 4096, 10)
 for i in range(4): call(i)
 for callers in (1, 4, 16):
     team = bench.Callers(callers)
-    team.run(call, 2 * callers)
+    team.run(call, 8 * callers)
     print(f"=== callers {callers}", file=sys.stderr, flush=True)
     secs, _ = team.run(call, 12 * callers)
     print(f"=== callers {callers}: {12 * callers * 4096 / secs / 1e6:.2f} M q/s", file=sys.stderr, flush=True)
