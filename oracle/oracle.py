@@ -17,6 +17,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "liboracle.so")
 REF_ENGINE = os.path.join(HERE, "_ref", "ref_engine")
+SHIM_ENGINE = os.path.join(HERE, "_ref", "shim_engine")  # INTEGRATION.md §1 compiled against the reference's header
 
 _lib = None
 
@@ -175,6 +176,23 @@ def query_terms(query: str) -> List[str]:
 
 def have_ref() -> bool:
     return os.path.exists(REF_ENGINE) and os.access(REF_ENGINE, os.X_OK)
+
+
+def have_shim() -> bool:
+    return os.path.exists(SHIM_ENGINE) and os.access(SHIM_ENGINE, os.X_OK)
+
+
+def shim_search(index_dir: str, queries: Sequence[str], k: int, timeout: float = 300) -> List[str]:
+    """cord19::Engine::reload()/search() of the compiled shim (reference header -> C ABI -> CUDA): the j.dump() texts."""
+    with tempfile.TemporaryDirectory() as td:
+        qf = os.path.join(td, "q.txt")
+        with open(qf, "w") as f:
+            for q in queries:
+                f.write(q.replace("\\", "\\\\").replace("\n", "\\n") + "\n")
+        out = os.path.join(td, "out.jsonl")
+        subprocess.run([SHIM_ENGINE, "search", index_dir, qf, str(k), out], check=True, timeout=timeout)
+        with open(out) as f:
+            return [json.loads(line)["text"] for line in f]
 
 
 def ref_write_segment(dump_path: str, segdir: str) -> None:

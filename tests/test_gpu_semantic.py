@@ -91,3 +91,16 @@ def test_invalid_utf8_query_is_refused_like_the_reference_throws(plain_index):
         eng.search_json_text(b"virus \xff\xfe", 10)
     assert ei.value.status == 1 and "UTF-8" in str(ei.value)
     eng.close()
+
+
+@pytest.mark.skipif(not orc.have_shim(), reason="oracle/_ref/shim_engine not built (needs /root/reference at build time)")
+@pytest.mark.parametrize("mode,k", [("expanded", 10), ("plain", 10), ("plain", 3)])
+def test_compiled_reference_side_shim_returns_the_reference_text(sem_index, plain_index, mode, k):
+    """INTEGRATION.md §1 as a real build: cord19::Engine::reload/search compiled against the REFERENCE's own
+    include/api_engine.hpp, delegating to the C ABI.  The nlohmann::json it returns, dumped by the reference's json
+    library, equals what the unmodified reference produced for the same index and queries."""
+    rows = GOLD[mode][str(k)]
+    texts = orc.shim_search(sem_index if mode == "expanded" else plain_index, [r["query"] for r in rows], k)
+    assert len(texts) == len(rows)
+    for row, text in zip(rows, texts):
+        assert text == row["text"], row["query"]
