@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnsb200.so")
+LIB_PATH = os.environ.get("NSB200_LIB") or os.path.join(_HERE, "libnsb200.so")  # NSB200_LIB: an experimental build
 
 NS_OK = 0
 NS_MAX_K = 100

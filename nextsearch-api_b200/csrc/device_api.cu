@@ -189,7 +189,7 @@ struct ns_batch {
     DevItem* d_items = nullptr;   // explicit items, or order[] when implicit_items
     uint32_t* d_counter = nullptr;
     uint32_t* d_qlock = nullptr;
-    uint32_t* d_qdone = nullptr;
+    unsigned long long* d_qdone = nullptr;
     uint32_t* d_npub = nullptr;
     size_t off_items = 0, up_bytes = 0, items_cap = 0, off_zero = 0, zero_bytes = 0;
     uint8_t* d_out = nullptr;  // hits | nhits | found, contiguous == h_out layout
@@ -269,8 +269,8 @@ KernelCfg pick_kernel_tk(bool fast, bool impact) {
 
 template <bool PUB>
 KernelCfg pick_kernel_p(uint32_t k, bool fast, bool impact, bool wide) {
-    if (wide) return k <= 16 ? pick_kernel_tk<kTileDocs, 16, 2, PUB>(fast, impact) : pick_kernel_tk<kTileDocs, 104, 2, PUB>(fast, impact);
-    return k <= 16 ? pick_kernel_tk<kTileDocs, 16, 1, PUB>(fast, impact) : pick_kernel_tk<kTileDocs, 104, 1, PUB>(fast, impact);
+    if (wide) return k <= 16 ? pick_kernel_tk<kTileDocs, 16, 2, PUB>(fast, impact) : pick_kernel_tk<kTileDocs, 100, 2, PUB>(fast, impact);
+    return k <= 16 ? pick_kernel_tk<kTileDocs, 16, 1, PUB>(fast, impact) : pick_kernel_tk<kTileDocs, 100, 1, PUB>(fast, impact);
 }
 
 // wide: some (query, segment) has more than 32 terms (two 32-term register groups per lane)
@@ -843,7 +843,8 @@ int finish_prepare(ns_index* idx, const std::shared_ptr<IndexState>& st, std::un
     b->off_items = off_dstart + sz_dstart;  // last uploaded region: only its used prefix is copied
     const size_t in_cap = b->off_items + sz_items;
     // zeroed per launch: queue head | locks[Q] | done[Q] | published | result blob
-    const size_t sz_ctrl = align_up((2 + 2 * (size_t)Q) * 4);
+    const size_t off_qdone = ((2 + (size_t)Q) * 4 + 7) / 8 * 8;  // u64 [Q] after queue head, published count and locks
+    const size_t sz_ctrl = align_up(off_qdone + (size_t)Q * 8);
     const size_t sz_hits = align_up(std::max<size_t>(1, (size_t)Q * k) * sizeof(ns_hit));
     const size_t sz_n = align_up(std::max<size_t>(1, Q) * 4);
     const size_t sz_found = align_up(std::max<size_t>(1, Q) * 8);
@@ -883,7 +884,7 @@ int finish_prepare(ns_index* idx, const std::shared_ptr<IndexState>& st, std::un
     b->d_counter = ctrl;
     b->d_npub = ctrl + 1;
     b->d_qlock = ctrl + 2;
-    b->d_qdone = ctrl + 2 + Q;
+    b->d_qdone = reinterpret_cast<unsigned long long*>(r.d_blob + b->off_zero + off_qdone);
     b->d_out = r.d_blob + b->off_zero + sz_ctrl;
     b->d_out_hits = reinterpret_cast<ns_hit*>(b->d_out);
     b->d_out_n = reinterpret_cast<uint32_t*>(b->d_out + b->off_n);
