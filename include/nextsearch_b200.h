@@ -324,6 +324,23 @@ int ns_engine_load_test(ns_engine* e, uint32_t nthreads, uint32_t per_thread, ui
 int ns_engine_cord_uid(const ns_engine* e, uint32_t seg, uint32_t doc, char* buf, size_t cap);
 
 /* ------------------------------------------------------------------ */
+/* Semantic expansion: similarity scan on the device.                  */
+/* (reference: SemanticIndex::most_similar_to_vec, the scan loop of    */
+/*  src/semantic_embedding.cpp:119-127)                                */
+/* ------------------------------------------------------------------ */
+typedef struct ns_semantic ns_semantic;
+/* vecs[rows][dim]: the L2-normalised vectors in row order (SemanticIndex::vecs, include/semantic_embedding.hpp:24). */
+int ns_semantic_upload(int device, uint32_t rows, uint32_t dim, const float* vecs, ns_semantic** out);
+void ns_semantic_destroy(ns_semantic* s);
+/* For each of the M query vectors qvecs[M][dim]: every row whose similarity is not below min_sim, with that
+ * similarity computed exactly as the reference's dot() does (sequential f32 multiply-then-add).  out_count[m] is the
+ * number of such rows; the first min(out_count[m], cap) are written to out_rows / out_sims [m][cap] in NO particular
+ * order (sort by row to replay the reference's scan order); out_count[m] > cap means the caller must rescan that vector
+ * with a larger cap or on the host.  Banned rows are the caller's to drop. */
+int ns_semantic_scan(ns_semantic* s, uint32_t M, const float* qvecs, float min_sim, uint32_t cap, uint32_t* out_rows,
+                     float* out_sims, uint32_t* out_count);
+
+/* ------------------------------------------------------------------ */
 /* Text + synthetic corpus tooling.                                    */
 /* ------------------------------------------------------------------ */
 

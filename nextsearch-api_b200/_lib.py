@@ -90,6 +90,9 @@ SYMBOLS = {
     "ns_batch_result_blob": (C.c_int, [_P, C.POINTER(_P), _u64p, _u64p, _u64p]),
     "ns_merge_blobs_device": (C.c_int, [C.c_int, C.c_uint32, C.c_int, C.c_uint32, _P, C.c_uint64, C.c_uint64, C.c_uint64,
                                         _P, _P, _P, _P]),
+    "ns_semantic_upload": (C.c_int, [C.c_int, C.c_uint32, C.c_uint32, _P, C.POINTER(_P)]),
+    "ns_semantic_destroy": (None, [_P]),
+    "ns_semantic_scan": (C.c_int, [_P, C.c_uint32, _P, C.c_float, C.c_uint32, _P, _P, _P]),
     "ns_selftest_fastdiv": (C.c_int, [C.c_int, C.c_uint64, C.c_uint64, _u64p]),
     "ns_engine_create": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(_P)]),
     "ns_engine_create_multi": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(_P)]),

@@ -16,6 +16,7 @@
 
 #include "../../include/nextsearch_b200.h"
 #include "bm25_kernels.cuh"
+#include "semantic_kernels.cuh"
 #include "device_internal.hpp"
 #include "host/common.hpp"
 #include "host/segment_io.hpp"
@@ -1542,6 +1543,96 @@ extern "C" int ns_exchange_fetch(ns_exchange* x, uint64_t step, uint32_t Q, int 
         if (out_nhits) std::memcpy(out_nhits, x->h_out + sz_hits, (size_t)Q * 4);
         if (out_found) std::memcpy(out_found, x->h_out + sz_hits + sz_n, (size_t)Q * 8);
     }
+    return NS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Semantic expansion: the similarity scan on the device (semantic_kernels.cuh)
+// ---------------------------------------------------------------------------------------------
+
+struct ns_semantic {
+    int device = 0;
+    uint32_t rows = 0, dim = 0;
+    float* d_vT = nullptr;  // [dim][rows]
+    std::mutex mu;          // one scan at a time per handle (scratch below)
+    float* d_q = nullptr;
+    uint32_t* d_rows = nullptr;
+    float* d_sims = nullptr;
+    uint32_t* d_count = nullptr;
+    uint32_t cap_m = 0, cap_per = 0;
+    cudaStream_t stream = nullptr;
+};
+
+extern "C" int ns_semantic_upload(int device, uint32_t rows, uint32_t dim, const float* vecs, ns_semantic** out) {
+    if (!out || !vecs || rows == 0 || dim == 0) { set_error("ns_semantic_upload: bad argument"); return NS_ERR_INVALID; }
+    *out = nullptr;
+    NS_CUDA(cudaSetDevice(device));
+    auto s = std::make_unique<ns_semantic>();
+    s->device = device;
+    s->rows = rows;
+    s->dim = dim;
+    std::vector<float> t((size_t)rows * dim);  // transpose on the host, once
+    for (uint32_t r = 0; r < rows; r++)
+        for (uint32_t i = 0; i < dim; i++) t[(size_t)i * rows + r] = vecs[(size_t)r * dim + i];
+    cudaError_t e = cudaMalloc(&s->d_vT, t.size() * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(s->d_vT, t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        if (s->d_vT) cudaFree(s->d_vT);
+        set_error(std::string("ns_semantic_upload: ") + cudaGetErrorString(e));
+        return NS_ERR_CUDA;
+    }
+    *out = s.release();
+    return NS_OK;
+}
+
+extern "C" void ns_semantic_destroy(ns_semantic* s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->stream) {
+        cudaStreamSynchronize(s->stream);
+        cudaStreamDestroy(s->stream);
+    }
+    for (void* p : {(void*)s->d_vT, (void*)s->d_q, (void*)s->d_rows, (void*)s->d_sims, (void*)s->d_count})
+        if (p) cudaFree(p);
+    delete s;
+}
+
+extern "C" int ns_semantic_scan(ns_semantic* s, uint32_t M, const float* qvecs, float min_sim, uint32_t cap,
+                                uint32_t* out_rows, float* out_sims, uint32_t* out_count) {
+    if (!s || !qvecs || !out_rows || !out_sims || !out_count || cap == 0) { set_error("ns_semantic_scan: bad argument"); return NS_ERR_INVALID; }
+    if (M == 0) return NS_OK;
+    std::lock_guard<std::mutex> lk(s->mu);
+    NS_CUDA(cudaSetDevice(s->device));
+    if (s->cap_m < M || s->cap_per < cap) {
+        for (void* p : {(void*)s->d_q, (void*)s->d_rows, (void*)s->d_sims, (void*)s->d_count})
+            if (p) cudaFree(p);
+        s->d_q = nullptr; s->d_rows = nullptr; s->d_sims = nullptr; s->d_count = nullptr;
+        const uint32_t cm = std::max(M, s->cap_m), cp = std::max(cap, s->cap_per);
+        NS_CUDA(cudaMalloc(&s->d_q, (size_t)cm * s->dim * sizeof(float)));
+        NS_CUDA(cudaMalloc(&s->d_rows, (size_t)cm * cp * 4));
+        NS_CUDA(cudaMalloc(&s->d_sims, (size_t)cm * cp * 4));
+        NS_CUDA(cudaMalloc(&s->d_count, (size_t)cm * 4));
+        s->cap_m = cm;
+        s->cap_per = cp;
+    }
+    const uint32_t cp = s->cap_per;
+    NS_CUDA(cudaMemcpyAsync(s->d_q, qvecs, (size_t)M * s->dim * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    NS_CUDA(cudaMemsetAsync(s->d_count, 0, (size_t)M * 4, s->stream));
+    const size_t smem = (size_t)kSemChunk * s->dim * sizeof(float);
+    if (smem > 48 * 1024) { set_error("ns_semantic_scan: embedding dimension too large for the query tile"); return NS_ERR_INVALID; }
+    cosine_scan_kernel<<<(s->rows + 255) / 256, 256, smem, s->stream>>>(s->d_vT, s->rows, s->dim, s->d_q, M, min_sim, cp, s->d_rows,
+                                                                        s->d_sims, s->d_count);
+    NS_CUDA(cudaGetLastError());
+    NS_CUDA(cudaMemcpyAsync(out_count, s->d_count, (size_t)M * 4, cudaMemcpyDeviceToHost, s->stream));
+    NS_CUDA(cudaStreamSynchronize(s->stream));
+    for (uint32_t m = 0; m < M; m++) {
+        const uint32_t n = std::min(out_count[m], cap);
+        if (n == 0) continue;
+        NS_CUDA(cudaMemcpyAsync(out_rows + (size_t)m * cap, s->d_rows + (size_t)m * cp, (size_t)n * 4, cudaMemcpyDeviceToHost, s->stream));
+        NS_CUDA(cudaMemcpyAsync(out_sims + (size_t)m * cap, s->d_sims + (size_t)m * cp, (size_t)n * 4, cudaMemcpyDeviceToHost, s->stream));
+    }
+    NS_CUDA(cudaStreamSynchronize(s->stream));
     return NS_OK;
 }
 

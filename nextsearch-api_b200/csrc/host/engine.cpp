@@ -42,6 +42,8 @@ using namespace nsb;
 
 namespace {
 
+thread_local bool tl_scan_failed = false;  // a device similarity scan of this thread's current query failed
+
 int hw_threads() {
     unsigned n = std::thread::hardware_concurrency();
     return n == 0 ? 1 : (int)n;
@@ -57,6 +59,7 @@ struct Generation {
     std::vector<std::shared_ptr<const void>> dev_state;  // per device slot: the committed device index
     MetaIndex meta;
     SemanticIndex sem;
+    std::shared_ptr<ns_semantic> sem_dev;  // the embeddings on device slot 0 (similarity scans of the expansion)
     double load_seconds = 0, upload_seconds = 0;
     uint64_t posting_bytes = 0;
 };
@@ -292,6 +295,44 @@ int do_reload(ns_engine* e) {
             const TermDict& dict = g->dict;
             g->sem.load(emb, [&](const std::string& w) { return dict.find(w.data(), w.size(), term_hash(w.data(), w.size())) >= 0; });
         }
+        if (g->sem.enabled && !e->devices.empty() && !std::getenv("NSB200_SEMANTIC_ON_HOST")) {
+            // the similarity scans run on the GPU (cosine_scan_kernel); sims are bit-identical to the host loop's
+            ns_semantic* h = nullptr;
+            if (ns_semantic_upload(e->devices[0], (uint32_t)g->sem.terms.size(), (uint32_t)g->sem.dim, g->sem.vecs.data(), &h) == NS_OK) {
+                g->sem_dev.reset(h, [](ns_semantic* p) { ns_semantic_destroy(p); });
+                const SemanticIndex* si = &g->sem;
+                g->sem.device_scan = [h, si](const float* qvecs, uint32_t M, float min_sim,
+                                             std::vector<std::vector<SemanticIndex::Survivor>>& out) {
+                    constexpr uint32_t cap = 4096;
+                    std::vector<uint32_t> rows((size_t)M * cap), count(M);
+                    std::vector<float> sims((size_t)M * cap);
+                    out.resize(M);
+                    (void)si;
+                    uint32_t use = cap;
+                    bool ok = ns_semantic_scan(h, M, qvecs, min_sim, use, rows.data(), sims.data(), count.data()) == NS_OK;
+                    uint32_t most = 0;
+                    for (uint32_t m = 0; ok && m < M; m++) most = std::max(most, count[m]);
+                    if (ok && most > use) {  // more survivors than room: scan again, on the device, with room for all
+                        use = most;
+                        rows.assign((size_t)M * use, 0u);
+                        sims.assign((size_t)M * use, 0.0f);
+                        ok = ns_semantic_scan(h, M, qvecs, min_sim, use, rows.data(), sims.data(), count.data()) == NS_OK;
+                    }
+                    if (!ok) {  // no host fallback behind a GPU engine: the search that asked fails with the CUDA error
+                        tl_scan_failed = true;
+                        for (auto& v : out) v.clear();
+                        return;
+                    }
+                    const uint32_t cap_used = use;
+                    for (uint32_t m = 0; m < M; m++) {
+                        const uint32_t cap = cap_used;
+                        out[m].resize(count[m]);
+                        for (uint32_t i = 0; i < count[m]; i++) out[m][i] = SemanticIndex::Survivor{rows[(size_t)m * cap + i], sims[(size_t)m * cap + i]};
+                        std::sort(out[m].begin(), out[m].end(), [](const SemanticIndex::Survivor& a, const SemanticIndex::Survivor& b) { return a.row < b.row; });
+                    }
+                };
+            }
+        }
     }
     e->last_reload.total_s = std::chrono::duration<double>(clk::now() - t0).count();
     e->last_reload.read_s = read_s;
@@ -438,6 +479,7 @@ struct ResolveScratch {
     std::vector<DevResolved> parts;
     std::vector<std::vector<ThreadOut>> per;
     std::vector<uint8_t> has;
+    std::atomic<int> failed{0};
 };
 
 template <class TermsOf>
@@ -469,12 +511,15 @@ void resolve_devices(ns_engine* e, const Generation& g, uint32_t Q, TermsOf term
         parts[p].scan_always = false;
     }
     has.assign(Q, 0);
+    sc.failed = 0;
     auto lo_of = [&](int t) { return (uint32_t)((uint64_t)Q * t / nt); };
     auto work = [&](int t) {
         std::vector<QueryTerm> qt;
         for (size_t p = 0; p < np; p++) per[t][p].terms.reserve((size_t)(lo_of(t + 1) - lo_of(t)) * 4 * std::max<size_t>(1, g.dev_cols[p].size()));
         for (uint32_t q = lo_of(t); q < lo_of(t + 1); q++) {
+            tl_scan_failed = false;
             has[q] = terms_of(q, qt) ? 1 : 0;
+            if (tl_scan_failed) sc.failed = 1;
             for (size_t p = 0; p < np; p++) {
                 ThreadOut& o = per[t][p];
                 const size_t before = o.terms.size();
@@ -598,6 +643,7 @@ int search_core(ns_engine* e, const std::shared_ptr<const Generation>& gen, uint
     using clk = std::chrono::steady_clock;
     const auto t0 = clk::now();
     resolve_devices(e, g, Q, terms_of, *scratch);
+    if (scratch->failed) { set_error("semantic expansion: the device similarity scan failed"); return NS_ERR_CUDA; }
     if (has_found && Q) std::memcpy(has_found, has.data(), Q);
     const auto t1 = clk::now();
     auto ms = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };

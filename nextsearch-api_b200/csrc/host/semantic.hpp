@@ -7,8 +7,8 @@
 // iteration over a std::unordered_map<std::string, float> filled in a particular sequence, then a (non-stable)
 // std::sort by weight.  The same containers, filled in the same sequence, are used here on purpose; everything
 // around them — file parsing, the similarity scan, the neighbour selection — is written for this code base:
-// the scan is a separable step (`Scanner`) so that the device kernel (cosine_scan_kernel, bm25_kernels.cuh)
-// can stand in for the host loop; both produce the survivors (sim >= min_sim, row not banned) in ascending row
+// the scan is a separable step (`Scanner`) so that the device kernel (cosine_scan_kernel, semantic_kernels.cuh)
+// can stand in for the host loop; both produce the survivors (sim not below min_sim) in ascending row
 // order with sims computed as the reference computes them (sequential f32 multiply-then-add, no FMA), and
 // the reference's bounded-heap selection is then replayed over the survivors only.
 #pragma once
@@ -39,9 +39,9 @@ struct SemanticIndex {
         uint32_t row;
         float sim;
     };
-    // survivors of one query vector, ascending row: sim(q, row) >= min_sim and !banned(row)
-    using Scanner = std::function<void(const float* qvec, float min_sim, const std::unordered_set<uint32_t>& banned,
-                                       std::vector<Survivor>& out)>;
+    // survivors of M query vectors (qvecs[M][dim]): per vector, every row whose sim is not below min_sim, ascending
+    // row.  Banned rows are dropped afterwards, on the host.
+    using Scanner = std::function<void(const float* qvecs, uint32_t M, float min_sim, std::vector<std::vector<Survivor>>& out)>;
     Scanner device_scan;  // set by the engine when the vectors are resident on a GPU; empty = host loop
 
     // the reference's constants (src/api_engine.cpp:412-417)
@@ -116,17 +116,20 @@ struct SemanticIndex {
         return it == term_to_row.end() ? nullptr : &vecs[(size_t)it->second * (size_t)dim];
     }
 
-    void host_scan(const float* qvec, float min_sim, const std::unordered_set<uint32_t>& banned, std::vector<Survivor>& out) const {
+    void host_scan_one(const float* qvec, float min_sim, std::vector<Survivor>& out) const {
         out.clear();
         const size_t nrows = terms.size();
         for (size_t r = 0; r < nrows; r++) {
-            if (banned.find((uint32_t)r) != banned.end()) continue;
             const float* v = &vecs[r * (size_t)dim];
             float s = 0.0f;
             for (int i = 0; i < dim; i++) s += qvec[i] * v[i];  // two roundings per step (the build uses -ffp-contract=off)
             if (s < min_sim) continue;
             out.push_back(Survivor{(uint32_t)r, s});
         }
+    }
+    void host_scan(const float* qvecs, uint32_t M, float min_sim, std::vector<std::vector<Survivor>>& out) const {
+        out.resize(M);
+        for (uint32_t m = 0; m < M; m++) host_scan_one(qvecs + (size_t)m * (size_t)dim, min_sim, out[m]);
     }
 
     // The reference keeps the best `topk` of the scan in a bounded min-heap and sorts it at the end
@@ -165,11 +168,6 @@ struct SemanticIndex {
             auto it = term_to_row.find(t);
             if (it != term_to_row.end()) banned.insert(it->second);
         }
-        std::vector<Survivor> surv, best;
-        auto scan = [&](const float* q) {
-            if (device_scan) device_scan(q, kMinSim, banned, surv);
-            else host_scan(q, kMinSim, banned, surv);
-        };
         auto offer = [&](const std::vector<Survivor>& nn, float cap) {
             for (const Survivor& s : nn) {
                 const std::string& cand = terms[s.row];
@@ -178,32 +176,39 @@ struct SemanticIndex {
                 if (it == w.end() || weight > it->second) w[cand] = weight;
             }
         };
-        // neighbours of every base term
+        // every vector this query scans with: one per base term that has a vector (in query order), then the
+        // normalised centroid of those — ONE batched scan (the reference scans once per vector)
+        std::vector<float> qbuf;
+        uint32_t nper = 0;
+        std::vector<float> centroid((size_t)dim, 0.0f);
         for (const auto& t : base) {
             const float* v = vec_of(t);
             if (!v) continue;
-            scan(v);
-            select_topk(surv, kPerTerm, best);
-            offer(best, kAlpha);
+            qbuf.insert(qbuf.end(), v, v + dim);
+            for (int j = 0; j < dim; j++) centroid[(size_t)j] += v[j];
+            nper++;
         }
-        // neighbours of the centroid of the base terms that have a vector
-        {
-            std::vector<float> q((size_t)dim, 0.0f);
-            int cnt = 0;
-            for (const auto& t : base) {
-                const float* v = vec_of(t);
-                if (!v) continue;
-                for (int j = 0; j < dim; j++) q[(size_t)j] += v[j];
-                cnt++;
-            }
-            if (cnt > 0) {
-                for (int j = 0; j < dim; j++) q[(size_t)j] /= (float)cnt;
-                l2_normalize(q);
-                scan(q.data());
-                select_topk(surv, kGlobalTopk, best);
-                offer(best, kAlpha * 0.8f);
-            }
+        if (nper > 0) {
+            for (int j = 0; j < dim; j++) centroid[(size_t)j] /= (float)nper;
+            l2_normalize(centroid);
+            qbuf.insert(qbuf.end(), centroid.begin(), centroid.end());
         }
+        std::vector<std::vector<Survivor>> surv;
+        const uint32_t M = nper > 0 ? nper + 1 : 0;
+        if (M) {
+            if (device_scan) device_scan(qbuf.data(), M, kMinSim, surv);
+            else host_scan(qbuf.data(), M, kMinSim, surv);
+        }
+        std::vector<Survivor> kept, best;
+        auto neighbours = [&](uint32_t m, int topk, float cap) {
+            kept.clear();
+            for (const Survivor& sv : surv[m])
+                if (banned.find(sv.row) == banned.end()) kept.push_back(sv);
+            select_topk(kept, topk, best);
+            offer(best, cap);
+        };
+        for (uint32_t m = 0; m < nper; m++) neighbours(m, kPerTerm, kAlpha);  // neighbours of every base term
+        if (nper > 0) neighbours(nper, kGlobalTopk, kAlpha * 0.8f);           // neighbours of the centroid
         std::vector<std::pair<std::string, float>> out;
         out.reserve(w.size());
         for (auto& kv : w) out.push_back(kv);

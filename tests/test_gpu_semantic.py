@@ -104,3 +104,50 @@ def test_compiled_reference_side_shim_returns_the_reference_text(sem_index, plai
     assert len(texts) == len(rows)
     for row, text in zip(rows, texts):
         assert text == row["text"], row["query"]
+
+
+def _write_random_embeddings(path, vocab, dim, nclusters, seed):
+    """Clustered vectors for terms t1..t<vocab>: members of a cluster are close (cosine ~0.7-0.95), clusters are far apart."""
+    rng = np.random.default_rng(seed)
+    centres = rng.normal(size=(nclusters, dim))
+    with open(path, "w", newline="") as f:
+        f.write(f"{vocab} {dim}\n")
+        for r in range(1, vocab + 1):
+            v = centres[r % nclusters] + rng.normal(scale=0.45, size=dim)
+            f.write(f"t{r} " + " ".join(f"{x:.5f}" for x in v) + "\n")
+
+
+def test_device_similarity_scan_gives_the_host_expansion_bit_for_bit(workdir):
+    """the expansion's similarity scans on the GPU (cosine_scan_kernel).  Same corpus and embeddings,
+    one engine with the scans on the device, one host-only engine with the host loop (which
+    tests/test_semantic_golden.py pins to the reference's expand): terms, weight bits and order must be identical,
+    and so must the searches that score those lists (CUDA vs the oracle's weighted entry)."""
+    from conftest import make_case
+    case = make_case(workdir, "sem_rand", nsb200.CorpusSpec(vocab=2500), 4000, 2)
+    emb = os.path.join(case.path, "embeddings.vec")
+    if not os.path.exists(emb):
+        _write_random_embeddings(emb, 2400, 24, 160, 5)
+    gpu = nsb200.Engine(case.path, device=0)
+    assert gpu.reload(), gpu.last_error
+    host = nsb200.Engine(case.path, device=None)
+    assert host.reload(), host.last_error
+    queries = nsb200.make_queries(case.spec, 150, 1, 4, seed=91) + ["t1", "t7 t7", "t2400 t3", "nosuch t5"]
+    expanded = 0
+    lists = []
+    for q in queries:
+        a, b = gpu.expand(q), host.expand(q)
+        assert a is not None and b is not None
+        assert [(t, np.float32(w).view(np.uint32)) for t, w in a] == [(t, np.float32(w).view(np.uint32)) for t, w in b], q
+        expanded += len(a) > len(set(q.split()))
+        lists.append(a)
+    assert expanded > 20  # the fixture really produces neighbours
+    oi = orc.OracleIndex(case.path)
+    res = gpu.search_batch(queries, 10)  # expansion (device scans) + weighted scoring, end to end
+    for i, q in enumerate(queries):
+        want = oi.search_weighted(lists[i], 10)
+        n = len(want["results"])
+        assert int(res.nhits[i]) == n and int(res.found[i]) == (want["found"] or 0), q
+        assert res.hits["score"][i, :n].view(np.uint32).tolist() == [h["score_bits"] for h in want["results"]], q
+        assert res.hits["doc"][i, :n].tolist() == [h["docId"] for h in want["results"]], q
+    gpu.close()
+    host.close()
