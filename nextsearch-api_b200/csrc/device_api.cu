@@ -937,6 +937,9 @@ int nsb::batch_prepare_on(ns_index* idx, const std::shared_ptr<const void>& stat
     for (auto& sg : st->segs) {
         fast = fast && sg.norm_in_range;
         all_raw = all_raw && (sg.d_post != nullptr || sg.P == 0);
+        // a doc-length factor outside the validated range may be negative or NaN (e.g. avgdl <= 0 in stats.bin): term
+        // scores can then be negative and partial sums are not monotone -> dense selection per tile
+        if (!sg.norm_in_range) scan_always = true;
     }
     uint32_t memo_seg = 0xFFFFFFFFu;
     int64_t memo_slot = -1;
@@ -1016,9 +1019,11 @@ int nsb::batch_prepare_trusted(ns_index* idx, const std::shared_ptr<const void>&
     std::shared_ptr<IndexState> st = std::const_pointer_cast<IndexState>(std::static_pointer_cast<const IndexState>(state));
     if (!st) { set_error("ns_batch_prepare: index has no committed segments"); return NS_ERR_STATE; }
     bool fast = pb.unit_weights;
+    bool scan_always = pb.scan_always;
     for (auto& sg : st->segs) {
         if (!sg.d_imp && sg.P) { set_error("batch_prepare_trusted: a segment has no resident scores"); return NS_ERR_STATE; }
         fast = fast && sg.norm_in_range;
+        if (!sg.norm_in_range) scan_always = true;  // see batch_prepare_on
     }
     if (pb.max_in_seg > NS_MAX_TERMS) { set_error("ns_batch_prepare: more than NS_MAX_TERMS terms for one (query, segment)"); return NS_ERR_INVALID; }
     NS_CUDA(cudaSetDevice(idx->device));
@@ -1030,7 +1035,7 @@ int nsb::batch_prepare_trusted(ns_index* idx, const std::shared_ptr<const void>&
     const std::vector<DevDistinct> dist;
     const std::vector<uint32_t> dstart(1, 0u);
     return finish_prepare(idx, st, std::move(b), Q, k, reinterpret_cast<const DevTerm*>(pb.terms), pb.qoff[Q], pb.qoff, dist, dstart,
-                          0, total_post, 0, pb.qoff[Q], pb.max_in_seg, pb.scan_always, fast, false, out);
+                          0, total_post, 0, pb.qoff[Q], pb.max_in_seg, scan_always, fast, false, out);
 }
 
 extern "C" int ns_batch_prepare(ns_index* idx, uint32_t Q, int k_in, const uint64_t* q_off, const ns_qterm* terms,
