@@ -524,11 +524,11 @@ def ours(args, rank, world, local_rank):
         multi = eng
     else:
         # (a) one process per GPU: every rank runs the pipeline (host front end of batch i+1 under the GPUs' batch i)
-        for r in searcher.search_many([batches[i % nb] for i in range(2)], TOPK):
+        for r in searcher.search_many([(packed[i % nb], BATCH_Q) for i in range(2)], TOPK):
             pass
         dist.barrier(group=gloo)
         t1 = time.perf_counter()
-        res = searcher.search_many([batches[i % nb] for i in range(e2e_steps)], TOPK)
+        res = searcher.search_many([(packed[i % nb], BATCH_Q) for i in range(e2e_steps)], TOPK)
         torch.cuda.synchronize(dev)
         per_rank_s = time.perf_counter() - t1
         t = torch.tensor([per_rank_s], device=f"cuda:{dev}")

@@ -288,6 +288,10 @@ int ns_engine_resolve_batch(ns_engine* e, uint32_t Q, const char* const* queries
 int ns_engine_resolve_batch_packed(ns_engine* e, uint32_t Q, const char* zqueries, size_t nbytes,
                                    uint64_t* q_off, ns_qterm* terms, uint64_t terms_cap, uint64_t* n_terms,
                                    uint8_t* has_terms);
+/* Front end + prepare without the launch, on a one-device engine: tokenise, dictionary, descriptors, H2D.  The caller
+ * launches (ns_batch_launch / ns_batch_launch_exchange), fetches and destroys the batch.  has_found as above. */
+int ns_engine_prepare_batch_packed(ns_engine* e, uint32_t Q, const char* zqueries, size_t nbytes, int k, ns_batch** out,
+                                   uint8_t* has_found);
 ns_index* ns_engine_index(ns_engine* e);                    /* device slot 0 */
 ns_index* ns_engine_device_index(ns_engine* e, int slot);
 /* timing and size of the last successful reload: total seconds, seconds in barrel reads + upload (overlapped),

@@ -119,6 +119,7 @@ SYMBOLS = {
     "ns_engine_resolve_batch_packed": (C.c_int, [_P, C.c_uint32, C.c_char_p, C.c_size_t, _P, _P, C.c_uint64, _u64p, _P]),
     "ns_engine_search_batch_packed": (C.c_int, [_P, C.c_uint32, C.c_char_p, C.c_size_t, C.c_int, _P, _P, _P, _P]),
     "ns_engine_resolve_batch": (C.c_int, [_P, C.c_uint32, _strs, _P, _P, C.c_uint64, _u64p, _P]),
+    "ns_engine_prepare_batch_packed": (C.c_int, [_P, C.c_uint32, C.c_char_p, C.c_size_t, C.c_int, C.POINTER(_P), _P]),
     "ns_engine_index": (_P, [_P]),
     "ns_engine_cord_uid": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_char_p, C.c_size_t]),
     "ns_text_query_terms": (C.c_int, [C.c_char_p, C.c_char_p, C.c_size_t]),

@@ -1,7 +1,7 @@
 // Deterministic synthetic CORD-19-shaped corpus + a streaming writer for the reference's
 // barrelized segment format.  This replaces include/segment_writer.hpp:23-169 of the reference
 // for corpora too large for its in-memory maps; tests check it byte-for-byte against the
-// reference's own SegmentWriter on small corpora (tests/test_writer_vs_reference.py).
+// reference's own SegmentWriter on small corpora (tests/test_oracle_golden.py: sha256 of all 133 files per segment).
 //
 // Corpus definition (recorded in BASELINE.md / DESIGN.md):
 //   term of rank r (1..V) is the string "t<r>";  p(r) ∝ 1/(r+q)^s

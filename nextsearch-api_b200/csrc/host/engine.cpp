@@ -1108,6 +1108,39 @@ extern "C" int ns_engine_search_batch_packed(ns_engine* e, uint32_t Q, const cha
                        out_hits, out_nhits, out_found, has_found);
 }
 
+// Front end + prepare of a batch on a single-device engine, WITHOUT launching: tokenise, dictionary, kernel-form
+// records, pinned staging, H2D.  What a caller that drives the launch itself needs (nextsearch-api_b200/dist.py: one
+// process per GPU, launches ordered across ranks) — the same work ns_engine_search_batch_packed does before its launch.
+extern "C" int ns_engine_prepare_batch_packed(ns_engine* e, uint32_t Q, const char* zqueries, size_t nbytes, int k,
+                                              ns_batch** out, uint8_t* has_found) {
+    if (!e || !out || (Q && !zqueries)) { set_error("ns_engine_prepare_batch_packed: null argument"); return NS_ERR_INVALID; }
+    *out = nullptr;
+    if (e->idx.size() != 1) { set_error("ns_engine_prepare_batch_packed: needs an engine with exactly one device"); return NS_ERR_STATE; }
+    std::vector<const char*> starts;
+    if (!split_packed(zqueries, nbytes, Q, starts)) {
+        set_error("ns_engine_prepare_batch_packed: buffer holds fewer than Q NUL-terminated strings");
+        return NS_ERR_INVALID;
+    }
+    auto gen = e->snapshot();
+    if (!gen) { set_error("search before a successful reload"); return NS_ERR_STATE; }
+    const Generation& g = *gen;
+    ResolveScratch sc;
+    resolve_devices(e, g, Q, [&](uint32_t q, std::vector<QueryTerm>& qt) { return query_terms_of(g, starts[q], qt); }, sc);
+    if (sc.failed) { set_error("semantic expansion: the device similarity scan failed"); return NS_ERR_CUDA; }
+    if (has_found && Q) std::memcpy(has_found, sc.has.data(), Q);
+    const DevResolved& r = sc.parts[0];
+    PreparedBatch pb{r.qoff.data(), r.terms.data(), r.weight.data(), r.max_in_seg, r.unit, r.scan_always};
+    int rc = batch_prepare_trusted(e->idx[0], g.dev_state[0], Q, k, pb, out);
+    if (rc != NS_ERR_STATE) return rc;
+    // no resident scores on the device (NSB200_NO_RESIDENT): the generic, validating prepare
+    std::vector<uint64_t> q_off((size_t)Q + 1);
+    std::vector<ns_qterm> qt(std::max<size_t>(1, r.qoff[Q]));
+    for (uint32_t q = 0; q <= Q; q++) q_off[q] = r.qoff[q];
+    for (uint32_t i = 0; i < r.qoff[Q]; i++)
+        qt[i] = ns_qterm{g.dict.owned[g.dev_cols[0][r.terms[i].slot]], r.terms[i].row, r.terms[i].idf, r.terms[i].w};
+    return batch_prepare_on(e->idx[0], g.dev_state[0], Q, k, q_off.data(), qt.data(), out);
+}
+
 // Explicit qterms_w lists (the reference's vector<pair<string, float>> of src/api_engine.cpp:410-421), one per
 // query: t_off[Q+1] indexes terms[] / weights[].  No tokenisation, no filter, no expansion: exactly what the
 // scoring loop (:426-505) receives.

@@ -130,10 +130,14 @@ class ShardedSearcher:
     def reload(self) -> bool:
         return self.engine.reload()
 
-    def prepare(self, queries: Sequence[str], k: int) -> ShardedBatch:
-        q_off, terms, has = self.engine.resolve_batch(queries)
-        b = self.engine.index.prepare(q_off, terms, k)
-        sb = ShardedBatch(batch=b, has_found=has, Q=len(queries), k=clamp_k(k))
+    def prepare(self, queries, k: int, Q: Optional[int] = None) -> ShardedBatch:
+        """queries: a sequence of strings, or (with Q given) the already packed NUL-separated byte buffer."""
+        if isinstance(queries, (bytes, bytearray)):
+            z, nq = bytes(queries), int(Q)
+        else:
+            z, nq = Engine.pack_queries(queries), len(queries)
+        b, has = self.engine.prepare_batch_packed(z, nq, k)  # front end + descriptors + H2D in one C call
+        sb = ShardedBatch(batch=b, has_found=has, Q=nq, k=clamp_k(k))
         if self.mode == "nccl":
             torch = self.torch
             lib = _lib.load()
@@ -191,7 +195,7 @@ class ShardedSearcher:
         prepare, H2D) running while the GPUs work on batch i.  Every rank must call it with the same batches."""
         out, prev = [], None
         for qs in batches:
-            sb = self.prepare(qs, k)
+            sb = self.prepare(qs[0], k, qs[1]) if isinstance(qs, tuple) else self.prepare(qs, k)  # (packed bytes, Q) or strings
             self.launch(sb)
             if prev is not None:
                 out.append(self.fetch(prev))

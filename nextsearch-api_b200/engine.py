@@ -59,6 +59,13 @@ class Batch:
         self._h = h
         self._index = index  # keep the index alive
 
+    @classmethod
+    def _adopt(cls, handle, Q: int, k: int, keep_alive) -> "Batch":
+        b = cls.__new__(cls)
+        b._lib = _lib.load()
+        b.Q, b.k, b._h, b._index = int(Q), clamp_k(k), handle, keep_alive
+        return b
+
     def set_splits(self, splits: int) -> None:
         check(self._lib.ns_batch_set_splits(self._h, int(splits)))
 
@@ -422,6 +429,13 @@ class Engine:
         check(self._lib.ns_engine_search_batch_packed(self._h, Q, zqueries, len(zqueries), int(k), _ptr(hits), _ptr(nhits),
                                                       _ptr(found), _ptr(has)))
         return BatchResult(hits, nhits, found, has[:Q].astype(bool), K)
+
+    def prepare_batch_packed(self, zqueries: bytes, Q: int, k: int = 10) -> Tuple["Batch", np.ndarray]:
+        """ns_engine_prepare_batch_packed: front end + descriptors + H2D, no launch.  Returns (batch, has_found)."""
+        has = np.zeros(max(1, Q), dtype=np.uint8)
+        h = C.c_void_p()
+        check(self._lib.ns_engine_prepare_batch_packed(self._h, int(Q), zqueries, len(zqueries), int(k), C.byref(h), _ptr(has)))
+        return Batch._adopt(h, Q, k, self), has[:Q].astype(bool)
 
     def search_terms_batch(self, term_lists: Sequence[Sequence[Tuple[str, float]]], k: int = 10) -> BatchResult:
         """Explicit (term, qweight) lists — the reference's qterms_w — one per query (ns_engine_search_terms_batch)."""
