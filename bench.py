@@ -393,6 +393,13 @@ def measure_e2e(call, e2e_steps, callers):
     return single_s, multi_s, n, (last2 if last2 is not None else last)
 
 
+def own_copy(res):
+    """A BatchResult that does not alias a caller thread's reusable buffers."""
+    import nsb200
+
+    return nsb200.BatchResult(res.hits.copy(), res.nhits.copy(), res.found.copy(), res.has_found.copy(), res.k)
+
+
 def oracle_parity(path, queries, result, k, nchk=256):
     import numpy as np
 
@@ -510,9 +517,17 @@ def ours(args, rank, world, local_rank):
     # ns_engine_search_batch_packed takes — what a request-coalescing front end accumulates.  Packing is done
     # once, outside the timed region, like any other host-side input preparation.
     packed = [nsb200.Engine.pack_queries(qs) for qs in batches]
+    tls = threading.local()
+
+    def out_buffers():
+        # every caller thread owns its host result buffers and reuses them, as a serving thread would
+        if not hasattr(tls, "out"):
+            tls.out = nsb200.Engine.result_buffers(BATCH_Q, TOPK)
+        return tls.out
+
     if world == 1:
         def call(i):
-            return eng.search_batch_packed(packed[i % nb], BATCH_Q, TOPK)
+            return eng.search_batch_packed(packed[i % nb], BATCH_Q, TOPK, out=out_buffers())
         callers = max(1, args.e2e_callers)
         single_s, e2e_s, n_multi, last = measure_e2e(call, e2e_steps, callers)
         e2e.update({"value": n_multi * BATCH_Q / e2e_s, "callers": callers, "calls": n_multi,
@@ -554,9 +569,21 @@ def ours(args, rank, world, local_rank):
         elif rank == 0:
 
             def call(i):
-                return multi.search_batch_packed(packed[i % nb], BATCH_Q, TOPK)
-            callers = max(1, args.e2e_callers, min(2 * world + 4, (os.cpu_count() or 8) // 2))
-            single_s, e2e_s, n_multi, last = measure_e2e(call, e2e_steps, callers)
+                return multi.search_batch_packed(packed[i % nb], BATCH_Q, TOPK, out=out_buffers())
+            # two caller counts (the box's host cores are shared by N device threads, the front-end pool and the callers);
+            # the better one is the headline, both are in the line
+            cap = max(1, (os.cpu_count() or 8) // 2)
+            tried = {}
+            best = None
+            for callers in sorted({max(1, args.e2e_callers, min(world + 4, cap)), max(1, args.e2e_callers, min(2 * world + 4, cap))}):
+                r = measure_e2e(call, e2e_steps, callers)
+                tried[str(callers)] = r[2] * BATCH_Q / r[1]
+                if best is None or tried[str(callers)] > best[0]:
+                    best = (tried[str(callers)], callers, r)
+            callers = best[1]
+            single_s, e2e_s, n_multi, last = best[2]
+            last = own_copy(last)
+            e2e["by_callers"] = tried
             e2e.update({"value": n_multi * BATCH_Q / e2e_s, "callers": callers, "calls": n_multi,
                         "single_caller_value": e2e_steps * BATCH_Q / single_s,
                         "path": "ns_engine_search_batch_packed on ONE engine handle spanning the N GPUs (ns_engine_create_multi, "

@@ -419,16 +419,21 @@ class Engine:
         (what a request-coalescing front end accumulates)."""
         return ("\0".join(queries) + "\0").encode("utf-8") if len(queries) else b""
 
-    def search_batch_packed(self, zqueries: bytes, Q: int, k: int = 10) -> BatchResult:
-        """ns_engine_search_batch_packed on an already packed host buffer."""
+    @staticmethod
+    def result_buffers(Q: int, k: int = 10):
+        """Caller-owned output buffers for search_batch_packed(out=...): a serving thread allocates them once and
+        reuses them for every call (fresh half-megabyte arrays per call are mmap'ed and unmapped by the allocator)."""
         K = clamp_k(k)
-        hits = np.empty((Q, K), dtype=HIT_DTYPE)
-        nhits = np.empty(Q, dtype=np.uint32)
-        found = np.empty(Q, dtype=np.uint64)
-        has = np.zeros(max(1, Q), dtype=np.uint8)
+        return (np.empty((Q, K), dtype=HIT_DTYPE), np.empty(Q, dtype=np.uint32), np.empty(Q, dtype=np.uint64),
+                np.zeros(max(1, Q), dtype=np.uint8))
+
+    def search_batch_packed(self, zqueries: bytes, Q: int, k: int = 10, out=None) -> BatchResult:
+        """ns_engine_search_batch_packed on an already packed host buffer; `out` = result_buffers(Q, k) to reuse."""
+        K = clamp_k(k)
+        hits, nhits, found, has = out if out is not None else self.result_buffers(Q, k)
         check(self._lib.ns_engine_search_batch_packed(self._h, Q, zqueries, len(zqueries), int(k), _ptr(hits), _ptr(nhits),
                                                       _ptr(found), _ptr(has)))
-        return BatchResult(hits, nhits, found, has[:Q].astype(bool), K)
+        return BatchResult(hits, nhits, found, has[:Q].view(np.bool_), K)
 
     def prepare_batch_packed(self, zqueries: bytes, Q: int, k: int = 10) -> Tuple["Batch", np.ndarray]:
         """ns_engine_prepare_batch_packed: front end + descriptors + H2D, no launch.  Returns (batch, has_found)."""
