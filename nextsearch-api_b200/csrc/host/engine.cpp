@@ -167,7 +167,7 @@ struct ns_engine {
     std::vector<std::unique_ptr<XGroup>> xg_pool;
     std::mutex sc_mu;
     std::vector<std::shared_ptr<void>> sc_pool;  // ResolveScratch objects (type-erased: defined further down)
-    std::unique_ptr<Coalescer> coalescer;
+    std::shared_ptr<Coalescer> coalescer;  // callers copy the pointer under co_mu: a stop cannot free it under them
     std::mutex co_mu;               // guards `coalescer` start/stop
     ReloadStats last_reload;
 
@@ -770,9 +770,12 @@ struct Coalescer {
     Coalescer(ns_engine* eng, uint32_t mb, uint32_t mw, int dispatchers) : e(eng), max_batch(std::max(1u, mb)), max_wait_us(mw) {
         for (int i = 0; i < std::max(1, dispatchers); i++) th.emplace_back([this] { loop(); });
     }
-    ~Coalescer() {
+    ~Coalescer() { shutdown(); }
+    // stop accepting, serve what is queued, join the dispatchers (idempotent)
+    void shutdown() {
         {
             std::lock_guard<std::mutex> lk(mu);
+            if (stop) return;
             stop = true;
         }
         cv_work.notify_all();
@@ -781,7 +784,7 @@ struct Coalescer {
     int submit_and_wait(Req& r) {
         r.t_in = std::chrono::steady_clock::now();
         std::unique_lock<std::mutex> lk(mu);
-        if (stop) { set_error("coalescer is stopping"); return NS_ERR_STATE; }
+        if (stop) return -1;  // stopped between the caller's look-up and now: the caller searches directly
         queue.push_back(&r);
         if (queue.size() == 1 || queue.size() >= max_batch) cv_work.notify_one();
         cv_done.wait(lk, [&] { return r.done; });
@@ -866,10 +869,10 @@ void Coalescer::loop() {
 // one query, through the coalescer when it runs; gen_out receives the generation the answer came from
 int search_one(ns_engine* e, const char* query, int k, ns_hit* hits, uint32_t* nhits, uint64_t* found, uint8_t* has,
                std::shared_ptr<const Generation>* gen_out) {
-    Coalescer* co = nullptr;
+    std::shared_ptr<Coalescer> co;
     {
         std::lock_guard<std::mutex> lk(e->co_mu);
-        co = e->coalescer.get();
+        co = e->coalescer;
     }
     if (co) {
         Coalescer::Req r;
@@ -880,7 +883,8 @@ int search_one(ns_engine* e, const char* query, int k, ns_hit* hits, uint32_t* n
         r.found = found;
         r.has = has;
         r.gen_out = gen_out;
-        return co->submit_and_wait(r);
+        const int rc = co->submit_and_wait(r);
+        if (rc >= 0) return rc;
     }
     auto gen = e->snapshot();
     if (gen_out) *gen_out = gen;
@@ -931,8 +935,12 @@ extern "C" int ns_engine_create(const char* index_dir, int device, ns_engine** o
 extern "C" void ns_engine_destroy(ns_engine* e) {
     if (!e) return;
     {
-        std::lock_guard<std::mutex> lk(e->co_mu);
-        e->coalescer.reset();  // drains and joins the dispatchers
+        std::shared_ptr<Coalescer> c;
+        {
+            std::lock_guard<std::mutex> lk(e->co_mu);
+            c = std::move(e->coalescer);
+        }
+        if (c) c->shutdown();  // drains and joins the dispatchers
     }
     e->dev_threads.clear();  // runs what is queued (batch teardowns), then joins
     e->xg_pool.clear();
@@ -1207,12 +1215,12 @@ extern "C" int ns_engine_coalescer_start(ns_engine* e, uint32_t max_batch, uint3
 
 extern "C" int ns_engine_coalescer_stop(ns_engine* e) {
     if (!e) return NS_ERR_INVALID;
-    std::unique_ptr<Coalescer> c;
+    std::shared_ptr<Coalescer> c;
     {
         std::lock_guard<std::mutex> lk(e->co_mu);
         c = std::move(e->coalescer);
     }
-    c.reset();  // serves what is queued, then joins
+    if (c) c->shutdown();  // serves what is queued, then joins; late submitters are refused, not left hanging
     return NS_OK;
 }
 

@@ -219,3 +219,27 @@ def test_drop_raw_segment_refuses_foreign_idf():
         idx.search_batch(np.array([0, 1], np.uint64), np.array([(0, 0, 0.123, 1.0)], dtype=nsb200.QTERM_DTYPE), 10)
     assert ei.value.status == 6
     idx.close()
+
+
+def test_negative_avgdl_segment_uses_dense_selection(workdir):
+    """stats.bin with avgdl < 0 (the reference reads it verbatim, src/api_segment.cpp:110-115): the doc-length factors
+    and with them some term scores are negative, partial sums are not monotone, so the threshold-crossing shortcut
+    must not be used.  Results still equal the oracle's, bit for bit."""
+    import struct
+
+    import fmt
+    idx = os.path.join(workdir, "neg_avgdl")
+    seg = os.path.join(idx, "segments", "seg_000001")
+    fmt.write_segment(seg, fmt.semantic_docs(0) + fmt.semantic_docs(1))
+    fmt.write_manifest(idx, ["seg_000001"])
+    with open(os.path.join(seg, "stats.bin"), "r+b") as f:
+        n = struct.unpack("<I", f.read(4))[0]
+        f.seek(0)
+        f.write(struct.pack("<If", n, -37.5))
+    eng = nsb200.Engine(idx, device=0)
+    assert eng.reload(), eng.last_error
+    oi = orc.OracleIndex(idx)
+    queries = ["virus", "covid vaccine", "bat virus spike", "fever cough rna lung", "mask masks ppe"]
+    for k in (3, 10, 100):
+        assert_same_as_oracle(eng.search_batch(queries, k), oi, queries, k)
+    eng.close()
