@@ -1071,6 +1071,11 @@ int launch_score(ns_batch* b, cudaStream_t s, const PublishDest* d_pub, uint32_t
     NS_CUDA(cudaStreamWaitEvent(s, b->res->ev_h2d, 0));
     NS_CUDA(cudaEventRecord(b->res->ev[0], s));
     if (b->Q > 0) {
+        // One memset: queue head, locks, completion counters AND the shared result lists.  The kernel relies on the lists
+        // starting as all-zero: items read hits[q][k-1] / nhits[q] WITHOUT the lock as a lower bound of the final k-th
+        // score, and a reader may see nhits == k before the entries another warp is writing are visible — what it then
+        // reads is either a former k-th score or this initial 0, both valid lower bounds while all scores are >= 0
+        // (batches with a negative weight or idf set scan_always and never take that shortcut).
         NS_CUDA(cudaMemsetAsync(b->res->d_blob + b->off_zero, 0, b->zero_bytes, s));
         ScoreArgs a;
         a.segs = b->st->d_segs;
