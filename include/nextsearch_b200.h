@@ -99,7 +99,11 @@ int ns_index_add_segment(ns_index* idx, uint32_t global_seg, uint32_t N, float a
  *                ever stored df != count.
  *   flags        NS_SEG_DROP_RAW: keep only {docId, resident term score} per posting (built in place); halves
  *                the segment's footprint.  A batch that names a row with an idf different from the resident
- *                one is then refused with NS_ERR_STATE. */
+ *                one is then refused with NS_ERR_STATE.
+ * Rows that SHARE postings (two lexicon entries pointing at overlapping ranges — legal for the reference, whose
+ * loop only follows (offset, count), src/api_engine.cpp:469-476) cannot have one resident score per posting:
+ * such a segment gets no resident scores and keeps its raw postings whatever the flags say; its terms are scored
+ * through the per-batch pre-pass, each row under its own idf. */
 #define NS_SEG_DROP_RAW 1u
 int ns_index_add_segment_ex(ns_index* idx, uint32_t global_seg, uint32_t N, float avgdl,
                             const uint32_t* doc_len, uint32_t T, const uint64_t* term_begin,

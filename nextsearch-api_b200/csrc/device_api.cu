@@ -360,6 +360,21 @@ int add_segment_core(ns_index* idx, uint32_t global_seg, uint32_t N, float avgdl
         }
         begin32[t] = (uint32_t)term_begin[t];
     }
+    // One resident score per posting (and its in-place build) needs every posting to belong to at most one row.
+    // Rows that share postings are legal for the reference — its loop only follows (offset, count),
+    // src/api_engine.cpp:469-476 — and would need one score per (row, posting): such a segment stays on the
+    // raw-posting path (no resident scores, {docId, tf} kept whatever the flags say; the per-batch pre-pass
+    // evaluates each named row under its own idf).
+    bool rows_overlap = false;
+    {
+        std::vector<uint32_t> by_begin;
+        by_begin.reserve(T);
+        for (uint32_t t = 0; t < T; t++)
+            if (term_count[t]) by_begin.push_back(t);
+        std::sort(by_begin.begin(), by_begin.end(), [&](uint32_t a, uint32_t b) { return begin32[a] < begin32[b]; });
+        for (size_t i = 1; i < by_begin.size() && !rows_overlap; i++)
+            rows_overlap = (uint64_t)begin32[by_begin[i - 1]] + term_count[by_begin[i - 1]] > begin32[by_begin[i]];
+    }
     s.gseg = global_seg;
     s.ndocs = N;
     s.T = T;
@@ -469,7 +484,7 @@ int add_segment_core(ns_index* idx, uint32_t global_seg, uint32_t N, float avgdl
     // df = LexEntry.count, what every writer stores: include/segment_writer.hpp:147-149).  A query term whose
     // idf differs bit-wise from the row's goes through the per-batch pre-pass, which needs the raw postings.
     const bool drop_raw = (flags & NS_SEG_DROP_RAW) != 0u;
-    if (P && T && !idx->sh->tun.no_resident) {
+    if (P && T && !idx->sh->tun.no_resident && !rows_overlap) {
         std::vector<float> h_idf(T);
         s.h_idf_bits.resize(T);
         for (uint32_t t = 0; t < T; t++) {

@@ -718,11 +718,21 @@ int search_core(ns_engine* e, const std::shared_ptr<const Generation>& gen, uint
     std::string keep = rc != NS_OK ? std::string(ns_last_error()) : std::string();
     // Teardown (waits for that device's kernels, returns the buffers to the device's pool) on the device threads;
     // nothing below depends on it.  The batches hold their generation's device state alive until then.
+    // A FAILED call drops its exchange group below, and the other devices' score kernels may still be storing
+    // into the root's gather buffer: the teardowns (which wait for those kernels) must have run before the
+    // group's memory is freed.
+    int live = 0;
+    for (size_t d = 0; d < ndev; d++) live += bs[d] ? 1 : 0;
+    auto torn_down = std::make_shared<Latch>(live);
     for (size_t d = 0; d < ndev; d++)
         if (bs[d]) {
             ns_batch* b = bs[d];
-            e->dev_threads[d]->submit([b] { ns_batch_destroy(b); });
+            e->dev_threads[d]->submit([b, torn_down] {
+                ns_batch_destroy(b);
+                torn_down->done();
+            });
         }
+    if (rc != NS_OK && live) torn_down->wait();
     if (e->trace)
     {
         double sp = 0, sl = 0;

@@ -229,3 +229,96 @@ def metadata_csv_text() -> str:
         'uid1_07,t7,PMC,Single name,10.2/h,2018-07,"Aristotle",Mind,https://c.example/7;',
     ]
     return hdr + "\n" + "\n".join(rows) + "\n"
+
+
+# ---- "odd" lexicon: entries no writer of the reference produces but its loader and scoring loop accept
+# ---- (tests/golden/odd.json holds what the reference itself returns for them) ----
+
+def write_segment_raw(segdir: str, stats_n: int, avgdl: float, docs: Sequence[Tuple[str, int]],
+                      entries: Sequence[Tuple[int, str, int, int, Sequence[Tuple[int, int]]]], legacy: bool = False) -> None:
+    """A segment whose stats.bin, docs.bin and lexicon entries are given verbatim.
+    docs: (cord_uid, doc_len); entries: (barrel, term, termId, df, postings) in file order — LexEntry.count is
+    len(postings) while df is whatever the caller says (src/api_engine.cpp:458-461 read df, :473 reads count).
+    `postings` may be the index of an earlier entry instead: the new entry then shares that entry's (offset, count)."""
+    import numpy as np
+
+    os.makedirs(segdir, exist_ok=True)
+    with open(os.path.join(segdir, "stats.bin"), "wb") as f:
+        f.write(struct.pack("<I", stats_n) + np.float32(avgdl).tobytes())
+    with open(os.path.join(segdir, "docs.bin"), "wb") as f:
+        f.write(struct.pack("<I", len(docs)))
+        for uid, dl in docs:
+            f.write(_s(uid) + _s("") + _s("") + struct.pack("<I", dl))
+    nb = 1 if legacy else BARRELS
+    lex: List[List[bytes]] = [[] for _ in range(nb)]
+    inv: List[List[bytes]] = [[] for _ in range(nb)]
+    offs = [0] * nb
+    placed = []  # per entry: (file, byte offset, count)
+    for barrel, term, tid, df, plist in entries:
+        if isinstance(plist, int):  # an ALIAS: the entry points at the posting list of the earlier entry `plist`
+            b, off, cnt = placed[plist]
+            lex[b].append(_s(term) + struct.pack("<IIQI", tid, df, off, cnt))
+            placed.append((b, off, cnt))
+            continue
+        b = 0 if legacy else barrel
+        lex[b].append(_s(term) + struct.pack("<IIQI", tid, df, offs[b], len(plist)))
+        inv[b].append(b"".join(struct.pack("<II", d, tf) for d, tf in plist))
+        placed.append((b, offs[b], len(plist)))
+        offs[b] += 8 * len(plist)
+    if legacy:
+        with open(os.path.join(segdir, "lexicon.bin"), "wb") as f:
+            f.write(struct.pack("<I", len(lex[0])) + b"".join(lex[0]))
+        with open(os.path.join(segdir, "inverted.bin"), "wb") as f:
+            f.write(b"".join(inv[0]))
+        return
+    with open(os.path.join(segdir, "barrels.bin"), "wb") as f:
+        f.write(struct.pack("<II", BARRELS, 1))
+    for b in range(BARRELS):
+        with open(os.path.join(segdir, f"lexicon_b{b:03d}.bin"), "wb") as f:
+            f.write(struct.pack("<I", len(lex[b])) + b"".join(lex[b]))
+        with open(os.path.join(segdir, f"inverted_b{b:03d}.bin"), "wb") as f:
+            f.write(b"".join(inv[b]))
+
+
+ODD_DOCS = [("o0", 4), ("o1", 9), ("o2", 2), ("o3", 7), ("o4", 5), ("o5", 3)]
+ODD_STATS_N = 10       # stats.bin N != number of docs in docs.bin: idf uses stats N (src/api_engine.cpp:461)
+ODD_AVGDL = 5.25       # stored verbatim, not the mean of the doc lengths (:478 reads seg.avgdl)
+ODD_ENTRIES = [
+    (0, "aa", 0, 3, [(0, 1), (2, 2), (5, 1)]),
+    (0, "bb", 1, 5, [(1, 3), (4, 1)]),          # df != count: idf from df, two postings streamed
+    (1, "cc", 2, 0, [(0, 1), (3, 1)]),          # df == 0: the term is skipped although it has postings (:458)
+    (1, "dd", 3, 12, [(2, 1), (3, 4)]),         # df > N: (N - df) wraps in u32 before the float conversion (:46)
+    (2, "ee", 4, 2, []),                        # usable term without postings
+    (3, "aa", 5, 1, [(4, 9)]),                  # the term again, later file: lex.emplace keeps the FIRST (api_segment.cpp:99)
+    (63, "ff", 6, 1, [(5, 2)]),
+    (63, "gg", 7, 6, [(0, 2), (1, 1), (2, 1), (3, 1), (4, 1), (5, 70000)]),   # tf >= 65536: unpacked device format
+]
+ODD_QUERIES = ["aa", "bb", "cc", "dd", "ee", "ff", "gg", "aa bb cc dd ee ff gg", "cc ee", "dd dd", "ff aa", "bb aa dd",
+               "gg aa", "cc"]
+
+
+def odd_second_segment_docs() -> List[Doc]:
+    """An ordinary second segment holding the same terms, so that the odd rows also meet the cross-segment top-k."""
+    return [
+        ("p0", 6, [("aa", 1), ("cc", 2)]),
+        ("p1", 3, [("bb", 1), ("dd", 1)]),
+        ("p2", 8, [("cc", 1), ("ee", 3), ("ff", 1)]),
+        ("p3", 5, [("aa", 2), ("dd", 2), ("gg", 1)]),
+    ]
+
+
+# Two more entries that SHARE the posting lists of "aa" and "gg" under other names and dfs: the reference only follows
+# (offset, count), so the same postings are scored with two different idfs.  (A separate index: on the device such
+# a segment cannot carry one resident score per posting and stays on the raw-posting path.)
+ALIAS_ENTRIES = ODD_ENTRIES + [
+    (0, "hh", 8, 2, 0),      # the list of "aa" (first entry), df 2 instead of 3
+    (63, "kk", 9, 1, 7),     # the list of "gg", df 1 instead of 6
+]
+ALIAS_QUERIES = ["hh", "aa hh", "hh aa", "kk gg", "kk", "aa bb hh kk", "hh hh"] + ODD_QUERIES[:8]
+
+
+def write_odd_index(index_dir: str, legacy: bool = False, alias: bool = False) -> None:
+    write_segment_raw(os.path.join(index_dir, "segments", "seg_000001"), ODD_STATS_N, ODD_AVGDL, ODD_DOCS,
+                      ALIAS_ENTRIES if alias else ODD_ENTRIES, legacy)
+    write_segment(os.path.join(index_dir, "segments", "seg_000002"), odd_second_segment_docs())
+    write_manifest(index_dir, ["seg_000001", "seg_000002"])

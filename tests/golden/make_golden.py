@@ -18,6 +18,9 @@ Outputs
                        reference's expanded (term, weight bits) list (SemanticIndex::expand), its results, and the
                        exact text of its JSON (j.dump()) including title / url / publish_time / author; the same
                        queries on the same index without the embeddings file (decoration only)
+  odd.json             a hand-written lexicon no writer produces but the reference's loader and scoring loop accept
+                       (tests/fmt.py: df != count, df == 0 with postings, df > N, an empty list, a term listed twice,
+                       stats N != docs, a stored avgdl that is not the mean, tf >= 65536), barrels and legacy layout
 """
 from __future__ import annotations
 
@@ -158,6 +161,19 @@ def main():
                     bits = [h[2] for h in r["hits"]]
                     assert len(set(bits)) == len(bits), ("score tie in the semantic fixture", r["query"])
         json.dump(sem, open(os.path.join(HERE, "semantic.json"), "w"), indent=0)
+        # ---- odd lexicon entries (hand-written files, read by the reference) ----
+        odd = {}
+        for legacy in (False, True):
+            odd_idx = os.path.join(td, f"odd_{int(legacy)}")
+            fmt.write_odd_index(odd_idx, legacy)
+            for k in (10, 2):
+                _, res = orc.ref_search(odd_idx, fmt.ODD_QUERIES, k)
+                odd[f"{'legacy' if legacy else 'barrels'}_{k}"] = compact(res, text=(k == 10))
+        alias_idx = os.path.join(td, "odd_alias")
+        fmt.write_odd_index(alias_idx, alias=True)      # two entries sharing one posting list
+        _, res = orc.ref_search(alias_idx, fmt.ALIAS_QUERIES, 10)
+        odd["alias_10"] = compact(res, text=True)
+        json.dump(odd, open(os.path.join(HERE, "odd.json"), "w"), indent=0)
         print("golden fixtures written to", HERE)
     finally:
         shutil.rmtree(td, ignore_errors=True)

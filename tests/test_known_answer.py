@@ -19,7 +19,7 @@ _libm.logf.argtypes = [ctypes.c_float]
 def idf(N, df):
     """bm25_idf: the reference calls std::log(float) = glibc logf (numpy's own float32 log may differ
     in the last bit, so call the same libm)."""
-    return f(_libm.logf(f(((f(np.uint32(N - df)) + f(0.5)) / (f(df) + f(0.5))) + f(1.0))))
+    return f(_libm.logf(f(((f(np.uint32((N - df) & 0xFFFFFFFF)) + f(0.5)) / (f(df) + f(0.5))) + f(1.0))))
 
 
 def term_score(idf_v, tf, dl, avgdl):
