@@ -47,7 +47,7 @@ typedef enum ns_status {
 } ns_status;
 
 #define NS_MAX_K 100          /* reference clamps k to 1..100: src/api_engine.cpp:377 */
-#define NS_MAX_TERMS 64       /* per (query, segment); reference expansion cap is 40: src/api_engine.cpp:417 */
+#define NS_MAX_TERMS 256      /* per (query, segment); the reference has no cap (its expansion stops at 40: src/api_engine.cpp:417) */
 #define NS_BARREL_COUNT 64    /* include/barrels.hpp:12 */
 
 /* thread-local text of the last error raised on this thread */

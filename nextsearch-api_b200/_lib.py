@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("NSB200_LIB") or os.path.join(_HERE, "libnsb200.so")  
 
 NS_OK = 0
 NS_MAX_K = 100
-NS_MAX_TERMS = 64
+NS_MAX_TERMS = 256
 NS_SEG_DROP_RAW = 1
 NS_IPC_HANDLE_BYTES = 64
 STATUS_NAMES = {0: "NS_OK", 1: "NS_ERR_INVALID", 2: "NS_ERR_CUDA", 3: "NS_ERR_IO", 4: "NS_ERR_FORMAT",

@@ -268,16 +268,36 @@ KernelCfg pick_kernel_tk(bool fast, bool impact) {
     return impact ? cfg_of<TDW, KCAP, false, true, NG, PUB>() : cfg_of<TDW, KCAP, false, false, NG, PUB>();
 }
 
-template <bool PUB>
-KernelCfg pick_kernel_p(uint32_t k, bool fast, bool impact, bool wide) {
-    if (wide) return k <= 16 ? pick_kernel_tk<kTileDocs, 16, 2, PUB>(fast, impact) : pick_kernel_tk<kTileDocs, 100, 2, PUB>(fast, impact);
-    return k <= 16 ? pick_kernel_tk<kTileDocs, 16, 1, PUB>(fast, impact) : pick_kernel_tk<kTileDocs, 100, 1, PUB>(fast, impact);
+template <int NG, bool PUB>
+KernelCfg pick_kernel_ng(uint32_t k, bool fast, bool impact) {
+    return k <= 16 ? pick_kernel_tk<kTileDocs, 16, NG, PUB>(fast, impact) : pick_kernel_tk<kTileDocs, 100, NG, PUB>(fast, impact);
 }
 
-// wide: some (query, segment) has more than 32 terms (two 32-term register groups per lane)
-// pub:  the score kernel publishes finished queries to peer GPUs (multi-GPU exchange)
-KernelCfg pick_kernel(uint32_t k, bool fast, bool impact, bool wide, bool pub) {
-    return pub ? pick_kernel_p<true>(k, fast, impact, wide) : pick_kernel_p<false>(k, fast, impact, wide);
+// The long-query variants (more than 64 terms in one (query, segment)) exist in the generic-arithmetic form only:
+// FAST differs from it by a cheaper, equally rounded division and a skipped multiplication by 1.0f, never in results.
+template <int TDW, int KCAP, int NG, bool PUB>
+KernelCfg pick_kernel_long(bool impact) {
+    return impact ? cfg_of<TDW, KCAP, false, true, NG, PUB>() : cfg_of<TDW, KCAP, false, false, NG, PUB>();
+}
+
+template <bool PUB>
+KernelCfg pick_kernel_p(uint32_t k, bool fast, bool impact, uint32_t ng) {
+    switch (ng) {
+        case 1: return pick_kernel_ng<1, PUB>(k, fast, impact);
+        case 2: return pick_kernel_ng<2, PUB>(k, fast, impact);
+        case 4: return k <= 16 ? pick_kernel_long<kTileDocs, 16, 4, PUB>(impact) : pick_kernel_long<kTileDocs, 100, 4, PUB>(impact);
+        default: return k <= 16 ? pick_kernel_long<kTileDocs, 16, 8, PUB>(impact) : pick_kernel_long<kTileDocs, 100, 8, PUB>(impact);
+    }
+}
+
+// 32-term register groups per lane for a batch whose largest (query, segment) term list has `max_in_seg` entries
+uint32_t term_groups(uint32_t max_in_seg) { return max_in_seg <= 32u ? 1u : max_in_seg <= 64u ? 2u : max_in_seg <= 128u ? 4u : 8u; }
+static_assert(NS_MAX_TERMS == 8 * 32, "the widest kernel variant holds 8 groups of 32 terms");
+
+// ng:  32-term register groups per lane (term_groups)
+// pub: the score kernel publishes finished queries to peer GPUs (multi-GPU exchange)
+KernelCfg pick_kernel(uint32_t k, bool fast, bool impact, uint32_t ng, bool pub) {
+    return pub ? pick_kernel_p<true>(k, fast, impact, ng) : pick_kernel_p<false>(k, fast, impact, ng);
 }
 
 // The dynamic shared-memory opt-in and the occupancy query of every kernel variant, done once per index
@@ -287,8 +307,8 @@ int init_kernel_table(IndexShared* idx) {
     for (int kk = 0; kk < 2; kk++)
         for (int fast = 0; fast < 2; fast++)
             for (int impact = 0; impact < 2; impact++)
-                for (int wp = 0; wp < 4; wp++) {
-                    const KernelCfg cfg = pick_kernel(kk ? 100u : 10u, fast != 0, impact != 0, (wp & 1) != 0, (wp & 2) != 0);
+                for (int wp = 0; wp < 8; wp++) {
+                    const KernelCfg cfg = pick_kernel(kk ? 100u : 10u, fast != 0, impact != 0, 1u << (wp & 3), (wp & 4) != 0);
                     int per_sm = 0;
                     NS_CUDA(cudaFuncSetAttribute(cfg.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
                     NS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cfg.fn, cfg.threads, cfg.smem));
@@ -1127,7 +1147,7 @@ int launch_score(ns_batch* b, cudaStream_t s, const PublishDest* d_pub, uint32_t
         a.q_done = b->d_qdone;
         a.n_published = b->d_npub;
         const bool fast = b->fast && !b->owner->tun.no_fast;
-        const KernelCfg cfg = pick_kernel(b->k, fast, b->impact, b->max_in_seg > 32u, d_pub != nullptr);
+        const KernelCfg cfg = pick_kernel(b->k, fast, b->impact, term_groups(b->max_in_seg), d_pub != nullptr);
         const uint32_t warps_per_block = (uint32_t)cfg.threads / 32u;
         int per_sm = 0;
         {

@@ -847,6 +847,36 @@ void Coalescer::loop() {
             rc = search_core(e, gen, Q, [&](uint32_t q, std::vector<QueryTerm>& qt) { return query_terms_of(g, take[q]->query, qt); },
                              K, hits.data(), nh.data(), fo.data(), has.data());
             if (rc != NS_OK) err = ns_last_error();
+            if (rc == NS_ERR_INVALID && Q > 1) {
+                // One request the device layer refuses (e.g. more than NS_MAX_TERMS terms) must not fail the strangers
+                // it happened to share a batch with: every request is served again on its own and gets its own status.
+                for (uint32_t q = 0; q < Q; q++) {
+                    Req* r = take[q];
+                    const int kr = std::max(1, std::min(r->k, NS_MAX_K));
+                    uint32_t n1 = 0;
+                    uint64_t f1 = 0;
+                    uint8_t h1 = 0;
+                    r->rc = search_core(e, gen, 1, [&](uint32_t, std::vector<QueryTerm>& qt) { return query_terms_of(g, r->query, qt); },
+                                        kr, hits.data(), &n1, &f1, &h1);
+                    if (r->rc != NS_OK) {
+                        r->err = ns_last_error();
+                        continue;
+                    }
+                    if (r->hits && n1) std::memcpy(r->hits, hits.data(), (size_t)n1 * sizeof(ns_hit));
+                    if (r->nhits) *r->nhits = n1;
+                    if (r->found) *r->found = f1;
+                    if (r->has) *r->has = h1;
+                    if (r->gen_out) *r->gen_out = gen;
+                }
+                n_batches++;
+                n_queries += Q;
+                {
+                    std::lock_guard<std::mutex> lk(mu);
+                    for (Req* r : take) r->done = true;
+                }
+                cv_done.notify_all();
+                continue;
+            }
         }
         n_batches++;
         n_queries += Q;

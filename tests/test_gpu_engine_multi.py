@@ -111,6 +111,46 @@ def test_coalescer_batches_single_requests(five_seg_case):
     eng.close()
 
 
+def test_coalescer_isolates_a_refused_request(five_seg_case):
+    """A request the device layer refuses (more than NS_MAX_TERMS terms for one segment) fails alone: the strangers
+    that shared its batch get their answers."""
+    eng = nsb200.Engine(five_seg_case.path, device=0)
+    assert eng.reload()
+    eng.coalescer_start(max_batch=64, max_wait_us=200000, dispatchers=1)   # long gather window: one batch for all
+    too_long = " ".join(f"t{i}" for i in range(1, 400))
+    queries = nsb200.make_queries(five_seg_case.spec, 15, 1, 4, seed=61)
+    got, errors, refused = {}, [], []
+
+    def worker(i):
+        try:
+            if i == 15:
+                try:
+                    eng.search_one(too_long, 10)
+                except nsb200._lib.NsError as ex:
+                    refused.append(ex.status)
+            else:
+                got[i] = eng.search_one(queries[i], 10)
+        except Exception as ex:  # noqa: BLE001
+            errors.append(repr(ex))
+
+    ths = [threading.Thread(target=worker, args=(i,)) for i in range(16)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    assert not errors, errors[:2]
+    assert refused == [1]                                   # NS_ERR_INVALID for the long query only
+    oi = five_seg_case.oracle
+    for i, q in enumerate(queries):
+        want = oi.search(q, 10)
+        hits, found = got[i]
+        assert found == want["found"], q
+        assert hits["score"].view(np.uint32).tolist() == [h["score_bits"] for h in want["results"]], q
+        assert hits["doc"].tolist() == [h["docId"] for h in want["results"]]
+    eng.coalescer_stop()
+    eng.close()
+
+
 def test_reload_swaps_generation_under_load(workdir):
     """Searches run while the index directory is switched to a DIFFERENT corpus and reloaded: every batch must
     equal the oracle on corpus A or on corpus B as a whole — never old lexicon rows against new device arrays."""

@@ -116,9 +116,29 @@ def test_more_than_32_terms_per_query(small_case, small_engine):
     qs = wide + nsb200.make_queries(small_case.spec, 40, 1, 5, seed=13) + EDGE_QUERIES
     for k in (10, 100):
         assert_same_as_oracle(small_engine.search_batch(qs, k), small_case.oracle, qs, k)
+
+
+def test_long_queries_up_to_256_terms(small_case, small_engine):
+    """The reference puts no cap on the number of query terms (a pasted paragraph is a legal query); up to
+    NS_MAX_TERMS = 256 terms per (query, segment) run the NG = 4 / NG = 8 kernel variants, mixed here with short
+    queries in one batch and alone, k = 10 and 100, also through a two-slot engine (the publishing variants)."""
+    import random
+
+    rng = random.Random(21)
+    long_qs = [" ".join(f"t{rng.randint(1, 600)}" for _ in range(n)) for n in (65, 100, 128, 129, 200, 256)]
+    long_qs.append(" ".join(f"t{i}" for i in range(1, 257)))             # 256 distinct head terms
+    long_qs.append(" ".join(["t3", "t7", "t11"] * 70))                   # 210 terms, three distinct
+    mixed = long_qs + nsb200.make_queries(small_case.spec, 24, 1, 5, seed=17) + EDGE_QUERIES
+    for k in (10, 100):
+        assert_same_as_oracle(small_engine.search_batch(mixed, k), small_case.oracle, mixed, k)
+    assert_same_as_oracle(small_engine.search_batch(long_qs[:2], 10), small_case.oracle, long_qs[:2], 10)   # NG = 4 alone
+    multi = nsb200.Engine(small_case.path, devices=[0, 0])
+    assert multi.reload(), multi.last_error
+    assert_same_as_oracle(multi.search_batch(mixed, 10), small_case.oracle, mixed, 10)
+    multi.close()
     # one more than the ABI limit is refused, not truncated
     with pytest.raises(nsb200._lib.NsError):
-        small_engine.search_batch([" ".join(f"t{i}" for i in range(1, 66))], 10)
+        small_engine.search_batch([" ".join(f"t{i}" for i in range(1, 258))], 10)
 
 
 def test_empty_and_termless_batches(small_case, small_engine):
