@@ -281,6 +281,12 @@ orc_index* orc_open(const char* index_dir) {
             ix->names = (char**)calloc((size_t)cap, sizeof(char*));
             while ((e = readdir(d))) {
                 if (strncmp(e->d_name, "seg_", 4) != 0) continue;
+                {   /* only directories (src/api_engine.cpp:64, e.is_directory() follows symlinks: stat, not lstat) */
+                    char sub[4400];
+                    struct stat sb;
+                    snprintf(sub, sizeof sub, "%s/%s", path, e->d_name);
+                    if (stat(sub, &sb) != 0 || !S_ISDIR(sb.st_mode)) continue;
+                }
                 if (ix->nseg == cap) { cap *= 2; ix->names = (char**)realloc(ix->names, sizeof(char*) * (size_t)cap); }
                 ix->names[ix->nseg++] = strdup(e->d_name);
             }
