@@ -293,8 +293,9 @@ ODD_ENTRIES = [
     (63, "ff", 6, 1, [(5, 2)]),
     (63, "gg", 7, 6, [(0, 2), (1, 1), (2, 1), (3, 1), (4, 1), (5, 70000)]),   # tf >= 65536: unpacked device format
 ]
+# (no query twice: the reference answers a repeated (query, k) from its LRU cache and marks it "from_cache")
 ODD_QUERIES = ["aa", "bb", "cc", "dd", "ee", "ff", "gg", "aa bb cc dd ee ff gg", "cc ee", "dd dd", "ff aa", "bb aa dd",
-               "gg aa", "cc"]
+               "gg aa", "cc cc dd"]
 
 
 def odd_second_segment_docs() -> List[Doc]:
