@@ -387,6 +387,15 @@ int ns_corpus_make_queries(const ns_corpus_spec* spec, uint64_t query_seed, uint
  * pseudo-random operand pairs drawn from the validated range; *mismatches must come back 0. */
 int ns_selftest_fastdiv(int device, uint64_t n, uint64_t seed, uint64_t* mismatches);
 
+/* Debug library only (libnsb200_dbg.so, built with -DNSB_DEBUG_CHECKS): the score kernel checks every index it
+ * derives from a posting, a tile table or a descriptor before using it — what the reference leaves unchecked
+ * (seg.docs[docId], src/api_engine.cpp:477) — and counts failures per class; counts[i] receives class i
+ * (0 item, 1 term descriptor, 2 tile window, 3 posting slice, 4 accumulator slot, 5 docId, 6 candidate, 7 result
+ * list).  The product library returns NS_ERR_STATE. */
+int ns_debug_violations(int device, uint64_t* counts, int n);
+/* Debug library only: fails ONE check of class 7 on purpose (the counters are live). */
+int ns_debug_selftest(int device);
+
 #ifdef __cplusplus
 }
 #endif

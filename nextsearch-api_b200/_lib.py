@@ -94,6 +94,8 @@ SYMBOLS = {
     "ns_semantic_destroy": (None, [_P]),
     "ns_semantic_scan": (C.c_int, [_P, C.c_uint32, _P, C.c_float, C.c_uint32, _P, _P, _P]),
     "ns_selftest_fastdiv": (C.c_int, [C.c_int, C.c_uint64, C.c_uint64, _u64p]),
+    "ns_debug_violations": (C.c_int, [C.c_int, _u64p, C.c_int]),
+    "ns_debug_selftest": (C.c_int, [C.c_int]),
     "ns_engine_create": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(_P)]),
     "ns_engine_create_multi": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(_P)]),
     "ns_engine_num_devices": (C.c_int, [_P]),

@@ -1681,6 +1681,40 @@ extern "C" int ns_semantic_scan(ns_semantic* s, uint32_t M, const float* qvecs, 
     return NS_OK;
 }
 
+// Debug build only (make debug -> libnsb200_dbg.so): the per-class counts of index checks that failed inside the
+// score kernel on `device` since the library was loaded (DbgClass in bm25_kernels.cuh).
+extern "C" int ns_debug_violations(int device, uint64_t* counts, int n) {
+    if (!counts || n < 0) { set_error("ns_debug_violations: bad argument"); return NS_ERR_INVALID; }
+#ifdef NSB_DEBUG_CHECKS
+    NS_CUDA(cudaSetDevice(device));
+    NS_CUDA(cudaDeviceSynchronize());
+    unsigned long long h[kDbgClasses];
+    NS_CUDA(cudaMemcpyFromSymbol(h, g_dbg_violations, sizeof(h)));
+    for (int i = 0; i < n; i++) counts[i] = i < (int)kDbgClasses ? h[i] : 0;
+    return NS_OK;
+#else
+    (void)device;
+    set_error("ns_debug_violations: not a debug build (make -C nextsearch-api_b200/csrc debug builds libnsb200_dbg.so)");
+    return NS_ERR_STATE;
+#endif
+}
+
+// Debug build only: one thread fails one check of the last class on purpose, so that a reader of
+// ns_debug_violations knows the counters are live (they must then show exactly one more "list" violation).
+extern "C" int ns_debug_selftest(int device) {
+#ifdef NSB_DEBUG_CHECKS
+    NS_CUDA(cudaSetDevice(device));
+    dbg_selftest_kernel<<<1, 1>>>(0);
+    NS_CUDA(cudaGetLastError());
+    NS_CUDA(cudaDeviceSynchronize());
+    return NS_OK;
+#else
+    (void)device;
+    set_error("ns_debug_selftest: not a debug build");
+    return NS_ERR_STATE;
+#endif
+}
+
 extern "C" int ns_selftest_fastdiv(int device, uint64_t n, uint64_t seed, uint64_t* mismatches) {
     if (!mismatches) return NS_ERR_INVALID;
     NS_CUDA(cudaSetDevice(device));
