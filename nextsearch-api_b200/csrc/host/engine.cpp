@@ -334,11 +334,13 @@ int do_reload(ns_engine* e) {
             }
         }
     }
-    e->last_reload.total_s = std::chrono::duration<double>(clk::now() - t0).count();
-    e->last_reload.read_s = read_s;
-    e->last_reload.dict_s = std::chrono::duration<double>(t2 - t1).count();
-    e->last_reload.posting_bytes = g->posting_bytes;
+    ReloadStats rs;
+    rs.total_s = std::chrono::duration<double>(clk::now() - t0).count();
+    rs.read_s = read_s;
+    rs.dict_s = std::chrono::duration<double>(t2 - t1).count();
+    rs.posting_bytes = g->posting_bytes;
     std::lock_guard<std::mutex> lk(e->gen_mu);
+    e->last_reload = rs;  // read by ns_engine_reload_stats under the same lock
     e->gen = g;  // in-flight calls keep the generation they started with
     return NS_OK;
 }
@@ -928,7 +930,7 @@ int search_one(ns_engine* e, const char* query, int k, ns_hit* hits, uint32_t* n
     }
     auto gen = e->snapshot();
     if (gen_out) *gen_out = gen;
-    if (!gen) { set_error("search before a successful reload"); return e->idx.empty() ? NS_ERR_STATE : NS_ERR_STATE; }
+    if (!gen) { set_error("search before a successful reload"); return NS_ERR_STATE; }
     const Generation& g = *gen;
     return search_core(e, gen, 1, [&](uint32_t, std::vector<QueryTerm>& qt) { return query_terms_of(g, query, qt); }, k, hits,
                        nhits, found, has);
@@ -1011,10 +1013,15 @@ extern "C" int ns_engine_reload(ns_engine* e) {
 extern "C" int ns_engine_reload_stats(const ns_engine* e, double* total_s, double* read_upload_s, double* dict_s,
                                       uint64_t* posting_bytes, uint64_t* device_bytes) {
     if (!e) return NS_ERR_INVALID;
-    if (total_s) *total_s = e->last_reload.total_s;
-    if (read_upload_s) *read_upload_s = e->last_reload.read_s;
-    if (dict_s) *dict_s = e->last_reload.dict_s;
-    if (posting_bytes) *posting_bytes = e->last_reload.posting_bytes;
+    ReloadStats rs;
+    {
+        std::lock_guard<std::mutex> lk(const_cast<ns_engine*>(e)->gen_mu);
+        rs = e->last_reload;
+    }
+    if (total_s) *total_s = rs.total_s;
+    if (read_upload_s) *read_upload_s = rs.read_s;
+    if (dict_s) *dict_s = rs.dict_s;
+    if (posting_bytes) *posting_bytes = rs.posting_bytes;
     if (device_bytes) {
         uint64_t b = 0;
         for (auto* ix : e->idx) b += ns_index_device_bytes(ix);
