@@ -481,6 +481,7 @@ struct ResolveScratch {
     std::vector<DevResolved> parts;
     std::vector<std::vector<ThreadOut>> per;
     std::vector<uint8_t> has;
+    std::vector<uint8_t> wide;   // [Q] 1: some (query, segment) has more than 32 terms (needs a wide kernel variant)
     std::atomic<int> failed{0};
 };
 
@@ -513,6 +514,7 @@ void resolve_devices(ns_engine* e, const Generation& g, uint32_t Q, TermsOf term
         parts[p].scan_always = false;
     }
     has.assign(Q, 0);
+    sc.wide.assign(Q, 0);
     sc.failed = 0;
     auto lo_of = [&](int t) { return (uint32_t)((uint64_t)Q * t / nt); };
     auto work = [&](int t) {
@@ -540,6 +542,7 @@ void resolve_devices(ns_engine* e, const Generation& g, uint32_t Q, TermsOf term
                         if (x.w != 1.0f || !(en.idf >= 9.094947017729282e-13f && en.idf <= 64.0f)) o.unit = false;
                     }
                     o.max_in_seg = std::max(o.max_in_seg, in_seg);
+                    if (in_seg > 32u) sc.wide[q] = 1;  // (a query is resolved by exactly one thread)
                 }
                 parts[p].qoff[q + 1] = (uint32_t)(o.terms.size() - before);
                 parts[p].weight[q] = wsum;
@@ -616,41 +619,16 @@ void release_group(ns_engine* e, std::unique_ptr<XGroup> g) {
     if (e->xg_pool.size() < 64) e->xg_pool.push_back(std::move(g));
 }
 
-template <class TermsOf>
-int search_core(ns_engine* e, const std::shared_ptr<const Generation>& gen, uint32_t Q, TermsOf terms_of, int k,
-                ns_hit* out_hits, uint32_t* out_nhits, uint64_t* out_found, uint8_t* has_found) {
-    if (e->idx.empty()) { set_error("engine was created without a CUDA device; there is no CPU search path"); return NS_ERR_STATE; }
-    if (!gen) { set_error("search before a successful reload"); return NS_ERR_STATE; }
-    const Generation& g = *gen;
+// Everything after the front end: prepare, launch, (exchange,) fetch of one resolved batch of Q queries.
+int run_resolved(ns_engine* e, const Generation& g, const std::vector<DevResolved>& parts, uint32_t Q, int k, ns_hit* out_hits,
+                 uint32_t* out_nhits, uint64_t* out_found, double resolve_ms) {
     const size_t ndev = e->idx.size();
-    std::shared_ptr<ResolveScratch> scratch;
-    {
-        std::lock_guard<std::mutex> lk(e->sc_mu);
-        if (!e->sc_pool.empty()) {
-            scratch = std::static_pointer_cast<ResolveScratch>(e->sc_pool.back());
-            e->sc_pool.pop_back();
-        }
-    }
-    if (!scratch) scratch = std::make_shared<ResolveScratch>();
-    struct GiveBack {
-        ns_engine* e;
-        std::shared_ptr<ResolveScratch>& s;
-        ~GiveBack() {
-            std::lock_guard<std::mutex> lk(e->sc_mu);
-            if (e->sc_pool.size() < 32) e->sc_pool.push_back(std::static_pointer_cast<void>(s));
-        }
-    } give_back{e, scratch};
-    std::vector<DevResolved>& parts = scratch->parts;
-    std::vector<uint8_t>& has = scratch->has;
     using clk = std::chrono::steady_clock;
-    const auto t0 = clk::now();
-    resolve_devices(e, g, Q, terms_of, *scratch);
-    if (scratch->failed) { set_error("semantic expansion: the device similarity scan failed"); return NS_ERR_CUDA; }
-    if (has_found && Q) std::memcpy(has_found, has.data(), Q);
     const auto t1 = clk::now();
     auto ms = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
     // prepare on device slot d: the trusted form; if the device index carries no resident scores
-    // (NSB200_NO_RESIDENT) the same terms go through the generic, validating ns_batch_prepare
+    // (NSB200_NO_RESIDENT, or a segment whose rows share postings) the same terms go through the generic, validating
+    // ns_batch_prepare
     auto prepare = [&](size_t d, ns_batch** out) -> int {
         const DevResolved& r = parts[d];
         PreparedBatch pb{r.qoff.data(), r.terms.data(), r.weight.data(), r.max_in_seg, r.unit, r.scan_always};
@@ -674,7 +652,7 @@ int search_core(ns_engine* e, const std::shared_ptr<const Generation>& gen, uint
         const auto t3 = clk::now();
         ns_batch_destroy(b);
         if (e->trace)
-            std::fprintf(stderr, "[nsb200] Q=%u resolve %.3f ms, prepare %.3f, launch+fetch %.3f, destroy %.3f\n", Q, ms(t0, t1),
+            std::fprintf(stderr, "[nsb200] Q=%u resolve %.3f ms, prepare %.3f, launch+fetch %.3f, destroy %.3f\n", Q, resolve_ms,
                          ms(t1, t2), ms(t2, t3), ms(t3, clk::now()));
         return rc;
     }
@@ -745,11 +723,98 @@ int search_core(ns_engine* e, const std::shared_ptr<const Generation>& gen, uint
         std::fprintf(stderr,
                      "[nsb200] Q=%u ndev=%zu resolve %.3f ms, prepare+launch %.3f (sum over devices: prepare %.3f, launch %.3f), "
                      "root merge enqueue %.3f, fetch(wait) %.3f, destroy %.3f\n",
-                     Q, ndev, ms(t0, t1), ms(t1, t2), sp, sl, ms(t2, t2b), ms(t2b, t3), ms(t3, clk::now()));
+                     Q, ndev, resolve_ms, ms(t1, t2), sp, sl, ms(t2, t2b), ms(t2b, t3), ms(t3, clk::now()));
     }
     if (rc == NS_OK) release_group(e, std::move(grp));  // a failed group is dropped: its flags may be in any state
     else set_error(keep);
     return rc;
+}
+
+// The queries `idx` of a resolved batch as a batch of their own (same per-device layout).
+void subset_parts(const std::vector<DevResolved>& parts, const std::vector<uint32_t>& idx, uint32_t max_in_seg_cap,
+                  std::vector<DevResolved>& out) {
+    out.assign(parts.size(), DevResolved{});
+    for (size_t p = 0; p < parts.size(); p++) {
+        const DevResolved& r = parts[p];
+        DevResolved& o = out[p];
+        o.qoff.assign(idx.size() + 1, 0);
+        o.weight.resize(idx.size());
+        size_t total = 0;
+        for (uint32_t q : idx) total += r.qoff[q + 1] - r.qoff[q];
+        o.terms.resize(std::max<size_t>(1, total));
+        size_t at = 0;
+        for (size_t i = 0; i < idx.size(); i++) {
+            const uint32_t q = idx[i];
+            const size_t n = r.qoff[q + 1] - r.qoff[q];
+            if (n) std::memcpy(o.terms.data() + at, r.terms.data() + r.qoff[q], n * sizeof(PreparedTerm));
+            at += n;
+            o.qoff[i + 1] = (uint32_t)at;
+            o.weight[i] = r.weight[q];
+        }
+        o.max_in_seg = std::min(r.max_in_seg, max_in_seg_cap);
+        o.unit = r.unit;                // flags of the whole batch: conservative for a part of it
+        o.scan_always = r.scan_always;
+    }
+}
+
+template <class TermsOf>
+int search_core(ns_engine* e, const std::shared_ptr<const Generation>& gen, uint32_t Q, TermsOf terms_of, int k,
+                ns_hit* out_hits, uint32_t* out_nhits, uint64_t* out_found, uint8_t* has_found) {
+    if (e->idx.empty()) { set_error("engine was created without a CUDA device; there is no CPU search path"); return NS_ERR_STATE; }
+    if (!gen) { set_error("search before a successful reload"); return NS_ERR_STATE; }
+    const Generation& g = *gen;
+    std::shared_ptr<ResolveScratch> scratch;
+    {
+        std::lock_guard<std::mutex> lk(e->sc_mu);
+        if (!e->sc_pool.empty()) {
+            scratch = std::static_pointer_cast<ResolveScratch>(e->sc_pool.back());
+            e->sc_pool.pop_back();
+        }
+    }
+    if (!scratch) scratch = std::make_shared<ResolveScratch>();
+    struct GiveBack {
+        ns_engine* e;
+        std::shared_ptr<ResolveScratch>& s;
+        ~GiveBack() {
+            std::lock_guard<std::mutex> lk(e->sc_mu);
+            if (e->sc_pool.size() < 32) e->sc_pool.push_back(std::static_pointer_cast<void>(s));
+        }
+    } give_back{e, scratch};
+    using clk = std::chrono::steady_clock;
+    const auto t0 = clk::now();
+    resolve_devices(e, g, Q, terms_of, *scratch);
+    if (scratch->failed) { set_error("semantic expansion: the device similarity scan failed"); return NS_ERR_CUDA; }
+    if (has_found && Q) std::memcpy(has_found, scratch->has.data(), Q);
+    const double resolve_ms = std::chrono::duration<double, std::milli>(clk::now() - t0).count();
+
+    // A few long queries must not put the whole batch on a wide kernel variant (one 40-term query among 4096 short
+    // ones costs the batch +22 %, one 250-term query 2.9 x: profiles/r2_long_query_probe.json): they are scored as a
+    // batch of their own, the short ones by the NG = 1 kernel, and the answers are put back in the caller's order.
+    uint32_t nwide = 0;
+    for (uint32_t q = 0; q < Q; q++) nwide += scratch->wide[q];
+    if (Q >= 256 && nwide != 0 && (uint64_t)nwide * 4 <= Q && out_hits && out_nhits && out_found) {
+        const uint32_t K = (uint32_t)std::max(1, std::min(k, NS_MAX_K));
+        std::vector<uint32_t> idx[2];
+        for (uint32_t q = 0; q < Q; q++) idx[scratch->wide[q]].push_back(q);
+        for (int cls = 0; cls < 2; cls++) {
+            std::vector<DevResolved> sub;
+            subset_parts(scratch->parts, idx[cls], cls == 0 ? 32u : 0xFFFFFFFFu, sub);
+            const uint32_t n = (uint32_t)idx[cls].size();
+            std::vector<ns_hit> h((size_t)n * K);
+            std::vector<uint32_t> nh(n);
+            std::vector<uint64_t> fo(n);
+            int rc = run_resolved(e, g, sub, n, k, h.data(), nh.data(), fo.data(), cls == 0 ? resolve_ms : 0.0);
+            if (rc != NS_OK) return rc;
+            for (uint32_t i = 0; i < n; i++) {
+                const uint32_t q = idx[cls][i];
+                std::memcpy(out_hits + (size_t)q * K, h.data() + (size_t)i * K, (size_t)K * sizeof(ns_hit));
+                out_nhits[q] = nh[i];
+                out_found[q] = fo[i];
+            }
+        }
+        return NS_OK;
+    }
+    return run_resolved(e, g, scratch->parts, Q, k, out_hits, out_nhits, out_found, resolve_ms);
 }
 
 // ------------------------------------------------------------------------------------------

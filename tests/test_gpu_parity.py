@@ -135,6 +135,13 @@ def test_long_queries_up_to_256_terms(small_case, small_engine):
     multi = nsb200.Engine(small_case.path, devices=[0, 0])
     assert multi.reload(), multi.last_error
     assert_same_as_oracle(multi.search_batch(mixed, 10), small_case.oracle, mixed, 10)
+    # a FEW long queries in a large batch are scored as a batch of their own (the short ones keep the NG = 1 kernel)
+    # and the answers come back in the caller's order: long queries first, last and in the middle
+    short = nsb200.make_queries(small_case.spec, 400, 1, 5, seed=19)
+    big = [long_qs[6]] + short[:150] + [long_qs[1], long_qs[3]] + short[150:] + EDGE_QUERIES + [long_qs[7]]
+    for k in (10, 100):
+        assert_same_as_oracle(small_engine.search_batch(big, k), small_case.oracle, big, k)
+    assert_same_as_oracle(multi.search_batch(big, 10), small_case.oracle, big, 10)
     multi.close()
     # one more than the ABI limit is refused, not truncated
     with pytest.raises(nsb200._lib.NsError):
