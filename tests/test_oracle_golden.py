@@ -113,11 +113,18 @@ def test_oracle_matches_live_reference(config1_case):
 
 
 @pytest.mark.ref
-def test_product_writer_matches_live_reference_writer(workdir):
-    spec = nsb200.CorpusSpec(vocab=1500, seed=99)
-    mine = os.path.join(workdir, "live_mine")
-    dump = os.path.join(workdir, "live_dump.bin")
-    nsb200.write_segment(spec, 700, 900, mine, True, dump)
-    ref = os.path.join(workdir, "live_ref")
+@pytest.mark.parametrize("vocab,seed,base,ndocs", [
+    (1500, 99, 700, 900),
+    (10, 3, 0, 40),          # T < 64: terms_per_barrel = 1, most barrels empty (include/barrels.hpp:26-30)
+    (64, 4, 5, 17),          # T == barrel count
+    (65, 5, 0, 1),           # a single document
+    (5000, 6, 123456, 300),  # T > 64 with a ragged last barrel
+])
+def test_product_writer_matches_live_reference_writer(workdir, vocab, seed, base, ndocs):
+    spec = nsb200.CorpusSpec(vocab=vocab, seed=seed)
+    mine = os.path.join(workdir, f"live_mine_{vocab}_{seed}")
+    dump = os.path.join(workdir, f"live_dump_{vocab}_{seed}.bin")
+    nsb200.write_segment(spec, base, ndocs, mine, True, dump)
+    ref = os.path.join(workdir, f"live_ref_{vocab}_{seed}")
     orc.ref_write_segment(dump, ref)
     assert sha_dir(mine) == sha_dir(ref)
