@@ -319,7 +319,7 @@ int init_kernel_table(IndexShared* idx) {
 
 }  // namespace
 
-extern "C" int ns_index_create(int device, ns_index** out) {
+static int ns_index_create_impl(int device, ns_index** out) {
     if (!out) { set_error("ns_index_create: out is null"); return NS_ERR_INVALID; }
     *out = nullptr;
     int n = 0;
@@ -346,6 +346,10 @@ extern "C" int ns_index_create(int device, ns_index** out) {
     }
     *out = idx;
     return NS_OK;
+}
+
+extern "C" int ns_index_create(int device, ns_index** out) {
+    return abi_guard("ns_index_create", NS_ERR_NOMEM, NS_ERR_STATE, [&]() -> int { return ns_index_create_impl(device, out); });
 }
 
 extern "C" void ns_index_destroy(ns_index* idx) {
@@ -556,7 +560,7 @@ int check_segment_args(ns_index* idx, uint32_t global_seg, uint32_t N, const uin
 
 }  // namespace
 
-extern "C" int ns_index_add_segment_ex(ns_index* idx, uint32_t global_seg, uint32_t N, float avgdl,
+static int ns_index_add_segment_ex_impl(ns_index* idx, uint32_t global_seg, uint32_t N, float avgdl,
                                        const uint32_t* doc_len, uint32_t T, const uint64_t* term_begin,
                                        const uint32_t* term_count, const float* row_idf, const void* postings,
                                        uint64_t P, uint32_t flags) {
@@ -577,6 +581,13 @@ extern "C" int ns_index_add_segment_ex(ns_index* idx, uint32_t global_seg, uint3
     return add_segment_core(idx, global_seg, N, avgdl, doc_len, T, term_begin, term_count, row_idf, d_post, P, flags);
 }
 
+extern "C" int ns_index_add_segment_ex(ns_index* idx, uint32_t global_seg, uint32_t N, float avgdl,
+                                       const uint32_t* doc_len, uint32_t T, const uint64_t* term_begin,
+                                       const uint32_t* term_count, const float* row_idf, const void* postings,
+                                       uint64_t P, uint32_t flags) {
+    return abi_guard("ns_index_add_segment_ex", NS_ERR_NOMEM, NS_ERR_STATE, [&]() -> int { return ns_index_add_segment_ex_impl(idx, global_seg, N, avgdl, doc_len, T, term_begin, term_count, row_idf, postings, P, flags); });
+}
+
 extern "C" int ns_index_add_segment(ns_index* idx, uint32_t global_seg, uint32_t N, float avgdl,
                                     const uint32_t* doc_len, uint32_t T, const uint64_t* term_begin,
                                     const uint32_t* term_count, const void* postings, uint64_t P) {
@@ -586,7 +597,7 @@ extern "C" int ns_index_add_segment(ns_index* idx, uint32_t global_seg, uint32_t
 // ---- streamed upload: the loader reads barrel files straight into pinned memory and pushes every
 // ---- finished range; the copies overlap the remaining file reads ----
 
-extern "C" int ns_upload_begin(ns_index* idx, uint64_t P, ns_upload** out) {
+static int ns_upload_begin_impl(ns_index* idx, uint64_t P, ns_upload** out) {
     if (!idx || !out) { set_error("ns_upload_begin: null argument"); return NS_ERR_INVALID; }
     *out = nullptr;
     if (P >= 0xFFFFFFFFull) { set_error("segment has >= 2^32 postings; split it"); return NS_ERR_INVALID; }
@@ -605,6 +616,10 @@ extern "C" int ns_upload_begin(ns_index* idx, uint64_t P, ns_upload** out) {
     }
     *out = u.release();
     return NS_OK;
+}
+
+extern "C" int ns_upload_begin(ns_index* idx, uint64_t P, ns_upload** out) {
+    return abi_guard("ns_upload_begin", NS_ERR_NOMEM, NS_ERR_STATE, [&]() -> int { return ns_upload_begin_impl(idx, P, out); });
 }
 
 extern "C" void* ns_upload_buffer(ns_upload* u) { return u ? u->h_pinned : nullptr; }
@@ -631,7 +646,7 @@ extern "C" void ns_upload_abort(ns_upload* u) {
     delete u;
 }
 
-extern "C" int ns_upload_finish(ns_upload* u, uint32_t global_seg, uint32_t N, float avgdl, const uint32_t* doc_len,
+static int ns_upload_finish_impl(ns_upload* u, uint32_t global_seg, uint32_t N, float avgdl, const uint32_t* doc_len,
                                 uint32_t T, const uint64_t* term_begin, const uint32_t* term_count,
                                 const float* row_idf, uint32_t flags) {
     if (!u) { set_error("ns_upload_finish: null"); return NS_ERR_INVALID; }
@@ -652,6 +667,12 @@ extern "C" int ns_upload_finish(ns_upload* u, uint32_t global_seg, uint32_t N, f
     return add_segment_core(idx, global_seg, N, avgdl, doc_len, T, term_begin, term_count, row_idf, d_post, P, flags);
 }
 
+extern "C" int ns_upload_finish(ns_upload* u, uint32_t global_seg, uint32_t N, float avgdl, const uint32_t* doc_len,
+                                uint32_t T, const uint64_t* term_begin, const uint32_t* term_count,
+                                const float* row_idf, uint32_t flags) {
+    return abi_guard("ns_upload_finish", NS_ERR_NOMEM, NS_ERR_STATE, [&]() -> int { return ns_upload_finish_impl(u, global_seg, N, avgdl, doc_len, T, term_begin, term_count, row_idf, flags); });
+}
+
 extern "C" int ns_index_abort(ns_index* idx) {
     if (!idx) return NS_ERR_INVALID;
     cudaSetDevice(idx->device);
@@ -661,7 +682,7 @@ extern "C" int ns_index_abort(ns_index* idx) {
     return NS_OK;
 }
 
-extern "C" int ns_index_commit(ns_index* idx) {
+static int ns_index_commit_impl(ns_index* idx) {
     if (!idx) { set_error("ns_index_commit: null"); return NS_ERR_INVALID; }
     NS_CUDA(cudaSetDevice(idx->device));
     std::lock_guard<std::mutex> lk(idx->mu);
@@ -704,6 +725,10 @@ extern "C" int ns_index_commit(ns_index* idx) {
     for (uint32_t i = 0; i < st->segs.size(); i++) st->slot_of[st->segs[i].gseg] = i;
     idx->live = st;  // in-flight batches keep their own shared_ptr to the old state
     return NS_OK;
+}
+
+extern "C" int ns_index_commit(ns_index* idx) {
+    return abi_guard("ns_index_commit", NS_ERR_NOMEM, NS_ERR_STATE, [&]() -> int { return ns_index_commit_impl(idx); });
 }
 
 extern "C" int ns_index_num_segments(const ns_index* idx) {
@@ -1073,10 +1098,15 @@ int nsb::batch_prepare_trusted(ns_index* idx, const std::shared_ptr<const void>&
                           0, total_post, 0, pb.qoff[Q], pb.max_in_seg, scan_always, fast, false, out);
 }
 
-extern "C" int ns_batch_prepare(ns_index* idx, uint32_t Q, int k_in, const uint64_t* q_off, const ns_qterm* terms,
+static int ns_batch_prepare_impl(ns_index* idx, uint32_t Q, int k_in, const uint64_t* q_off, const ns_qterm* terms,
                                 ns_batch** out) {
     if (!idx) { set_error("ns_batch_prepare: null argument"); return NS_ERR_INVALID; }
     return nsb::batch_prepare_on(idx, nsb::index_live_state(idx), Q, k_in, q_off, terms, out);
+}
+
+extern "C" int ns_batch_prepare(ns_index* idx, uint32_t Q, int k_in, const uint64_t* q_off, const ns_qterm* terms,
+                                ns_batch** out) {
+    return abi_guard("ns_batch_prepare", NS_ERR_NOMEM, NS_ERR_STATE, [&]() -> int { return ns_batch_prepare_impl(idx, Q, k_in, q_off, terms, out); });
 }
 
 extern "C" int ns_batch_set_splits(ns_batch* b, uint32_t splits) {
@@ -1253,7 +1283,7 @@ extern "C" float ns_batch_last_kernel_ms(ns_batch* b, int which) {
     return ms;
 }
 
-extern "C" int ns_search_batch(ns_index* idx, uint32_t Q, int k, const uint64_t* q_off, const ns_qterm* terms,
+static int ns_search_batch_impl(ns_index* idx, uint32_t Q, int k, const uint64_t* q_off, const ns_qterm* terms,
                                ns_hit* out_hits, uint32_t* out_nhits, uint64_t* out_found) {
     if (!idx) { set_error("ns_search_batch: null index"); return NS_ERR_INVALID; }
     auto now = [] { return std::chrono::steady_clock::now(); };
@@ -1275,6 +1305,11 @@ extern "C" int ns_search_batch(ns_index* idx, uint32_t Q, int k, const uint64_t*
                      nitems, ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, t4));
     }
     return rc;
+}
+
+extern "C" int ns_search_batch(ns_index* idx, uint32_t Q, int k, const uint64_t* q_off, const ns_qterm* terms,
+                               ns_hit* out_hits, uint32_t* out_nhits, uint64_t* out_found) {
+    return abi_guard("ns_search_batch", NS_ERR_NOMEM, NS_ERR_STATE, [&]() -> int { return ns_search_batch_impl(idx, Q, k, q_off, terms, out_hits, out_nhits, out_found); });
 }
 
 static int merge_launch(int device, uint32_t Q, int k_in, uint32_t nlists, const void* d_hits, const void* d_nhits,
@@ -1371,9 +1406,14 @@ int upload_pub(ns_exchange* x) {
 static int exchange_create_impl(int device, uint32_t world, uint32_t rank, uint32_t max_queries, uint32_t slots,
                                 bool publisher_only, ns_exchange** out);
 
-extern "C" int ns_exchange_create(int device, uint32_t world, uint32_t rank, uint32_t max_queries, uint32_t slots,
+static int ns_exchange_create_impl(int device, uint32_t world, uint32_t rank, uint32_t max_queries, uint32_t slots,
                                   ns_exchange** out) {
     return exchange_create_impl(device, world, rank, max_queries, slots, false, out);
+}
+
+extern "C" int ns_exchange_create(int device, uint32_t world, uint32_t rank, uint32_t max_queries, uint32_t slots,
+                                  ns_exchange** out) {
+    return abi_guard("ns_exchange_create", NS_ERR_NOMEM, NS_ERR_STATE, [&]() -> int { return ns_exchange_create_impl(device, world, rank, max_queries, slots, out); });
 }
 
 int nsb::exchange_create_publisher(int device, uint32_t world, uint32_t rank, uint32_t max_queries, uint32_t slots,
@@ -1608,7 +1648,7 @@ struct ns_semantic {
     cudaStream_t stream = nullptr;
 };
 
-extern "C" int ns_semantic_upload(int device, uint32_t rows, uint32_t dim, const float* vecs, ns_semantic** out) {
+static int ns_semantic_upload_impl(int device, uint32_t rows, uint32_t dim, const float* vecs, ns_semantic** out) {
     if (!out || !vecs || rows == 0 || dim == 0) { set_error("ns_semantic_upload: bad argument"); return NS_ERR_INVALID; }
     *out = nullptr;
     NS_CUDA(cudaSetDevice(device));
@@ -1631,6 +1671,10 @@ extern "C" int ns_semantic_upload(int device, uint32_t rows, uint32_t dim, const
     return NS_OK;
 }
 
+extern "C" int ns_semantic_upload(int device, uint32_t rows, uint32_t dim, const float* vecs, ns_semantic** out) {
+    return abi_guard("ns_semantic_upload", NS_ERR_NOMEM, NS_ERR_STATE, [&]() -> int { return ns_semantic_upload_impl(device, rows, dim, vecs, out); });
+}
+
 extern "C" void ns_semantic_destroy(ns_semantic* s) {
     if (!s) return;
     cudaSetDevice(s->device);
@@ -1643,7 +1687,7 @@ extern "C" void ns_semantic_destroy(ns_semantic* s) {
     delete s;
 }
 
-extern "C" int ns_semantic_scan(ns_semantic* s, uint32_t M, const float* qvecs, float min_sim, uint32_t cap,
+static int ns_semantic_scan_impl(ns_semantic* s, uint32_t M, const float* qvecs, float min_sim, uint32_t cap,
                                 uint32_t* out_rows, float* out_sims, uint32_t* out_count) {
     if (!s || !qvecs || !out_rows || !out_sims || !out_count || cap == 0) { set_error("ns_semantic_scan: bad argument"); return NS_ERR_INVALID; }
     if (M == 0) return NS_OK;
@@ -1679,6 +1723,11 @@ extern "C" int ns_semantic_scan(ns_semantic* s, uint32_t M, const float* qvecs, 
     }
     NS_CUDA(cudaStreamSynchronize(s->stream));
     return NS_OK;
+}
+
+extern "C" int ns_semantic_scan(ns_semantic* s, uint32_t M, const float* qvecs, float min_sim, uint32_t cap,
+                                uint32_t* out_rows, float* out_sims, uint32_t* out_count) {
+    return abi_guard("ns_semantic_scan", NS_ERR_NOMEM, NS_ERR_STATE, [&]() -> int { return ns_semantic_scan_impl(s, M, qvecs, min_sim, cap, out_rows, out_sims, out_count); });
 }
 
 // Debug build only (make debug -> libnsb200_dbg.so): the per-class counts of index checks that failed inside the

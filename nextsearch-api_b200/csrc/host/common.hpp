@@ -3,6 +3,8 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <exception>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -11,6 +13,24 @@ namespace nsb {
 // thread-local error text surfaced through ns_last_error()
 void set_error(const std::string& msg);
 const char* last_error();
+
+// No exception crosses the C ABI: every exported entry point that can allocate runs its body through this barrier
+// (std::bad_alloc -> `nomem`, anything else -> `other`; the text goes to ns_last_error()).
+template <class F>
+int abi_guard(const char* what, int nomem, int other, F&& body) noexcept {
+    try {
+        return body();
+    } catch (const std::bad_alloc&) {
+        try { set_error(std::string(what) + ": out of host memory"); } catch (...) {}
+        return nomem;
+    } catch (const std::exception& ex) {
+        try { set_error(std::string(what) + ": " + ex.what()); } catch (...) {}
+        return other;
+    } catch (...) {
+        try { set_error(std::string(what) + ": unknown exception"); } catch (...) {}
+        return other;
+    }
+}
 
 // ---- raw little-endian IO (format of include/indexio.hpp:8-29 in the reference:
 // u32/u64/f32 as host bytes, strings as u32 length + bytes) ----

@@ -517,7 +517,7 @@ void resolve_devices(ns_engine* e, const Generation& g, uint32_t Q, TermsOf term
     sc.wide.assign(Q, 0);
     sc.failed = 0;
     auto lo_of = [&](int t) { return (uint32_t)((uint64_t)Q * t / nt); };
-    auto work = [&](int t) {
+    auto work_body = [&](int t) {
         std::vector<QueryTerm> qt;
         for (size_t p = 0; p < np; p++) per[t][p].terms.reserve((size_t)(lo_of(t + 1) - lo_of(t)) * 4 * std::max<size_t>(1, g.dev_cols[p].size()));
         for (uint32_t q = lo_of(t); q < lo_of(t + 1); q++) {
@@ -549,7 +549,15 @@ void resolve_devices(ns_engine* e, const Generation& g, uint32_t Q, TermsOf term
             }
         }
     };
+    auto work = [&](int t) {   // pool threads: an exception (out of memory) must not escape them
+        try {
+            work_body(t);
+        } catch (...) {
+            sc.failed = 2;
+        }
+    };
     pool.run(nt, work);
+    if (sc.failed == 2) return;  // the caller reports it; the partial buffers are not used
     for (size_t p = 0; p < np; p++) {
         DevResolved& r = parts[p];
         for (uint32_t q = 0; q < Q; q++) r.qoff[q + 1] += r.qoff[q];
@@ -667,14 +675,19 @@ int run_resolved(ns_engine* e, const Generation& g, const std::vector<DevResolve
     std::vector<int> rcs(ndev, NS_OK);
     std::vector<std::string> errs(ndev);
     std::vector<double> t_prep(ndev, 0.0), t_launch(ndev, 0.0);
-    auto one = [&](int d) {
-        const auto a = clk::now();
-        rcs[d] = prepare((size_t)d, &bs[d]);
-        const auto b = clk::now();
-        if (rcs[d] == NS_OK) rcs[d] = ns_batch_launch_exchange(bs[d], grp->x[d], step, nullptr);
-        if (rcs[d] != NS_OK) errs[d] = ns_last_error();
-        t_prep[d] = ms(a, b);
-        t_launch[d] = ms(b, clk::now());
+    auto one = [&](int d) {   // runs on device thread d: nothing may escape it (the caller waits on the latch)
+        rcs[d] = abi_guard("device thread", NS_ERR_NOMEM, NS_ERR_STATE, [&]() -> int {
+            const auto a = clk::now();
+            int r = prepare((size_t)d, &bs[d]);
+            const auto b = clk::now();
+            if (r == NS_OK) r = ns_batch_launch_exchange(bs[d], grp->x[d], step, nullptr);
+            t_prep[d] = ms(a, b);
+            t_launch[d] = ms(b, clk::now());
+            return r;
+        });
+        if (rcs[d] != NS_OK) {
+            try { errs[d] = ns_last_error(); } catch (...) {}
+        }
     };
     {
         Latch latch((int)ndev);
@@ -783,6 +796,7 @@ int search_core(ns_engine* e, const std::shared_ptr<const Generation>& gen, uint
     using clk = std::chrono::steady_clock;
     const auto t0 = clk::now();
     resolve_devices(e, g, Q, terms_of, *scratch);
+    if (scratch->failed == 2) { set_error("front end: out of host memory"); return NS_ERR_NOMEM; }
     if (scratch->failed) { set_error("semantic expansion: the device similarity scan failed"); return NS_ERR_CUDA; }
     if (has_found && Q) std::memcpy(has_found, scratch->has.data(), Q);
     const double resolve_ms = std::chrono::duration<double, std::milli>(clk::now() - t0).count();
@@ -1007,7 +1021,7 @@ int search_one(ns_engine* e, const char* query, int k, ns_hit* hits, uint32_t* n
 // C ABI
 // ------------------------------------------------------------------------------------------
 
-extern "C" int ns_engine_create_multi(const char* index_dir, int ndev, const int* devices, ns_engine** out) {
+static int ns_engine_create_multi_impl(const char* index_dir, int ndev, const int* devices, ns_engine** out) {
     if (!index_dir || !out || ndev < 0 || (ndev > 0 && !devices) || ndev > NS_MAX_PEERS) {
         set_error("ns_engine_create_multi: bad argument");
         return NS_ERR_INVALID;
@@ -1032,6 +1046,10 @@ extern "C" int ns_engine_create_multi(const char* index_dir, int ndev, const int
 fail_cuda:
     for (auto* ix : e->idx) ns_index_destroy(ix);
     return NS_ERR_CUDA;
+}
+
+extern "C" int ns_engine_create_multi(const char* index_dir, int ndev, const int* devices, ns_engine** out) {
+    return abi_guard("ns_engine_create_multi", NS_ERR_NOMEM, NS_ERR_STATE, [&]() -> int { return ns_engine_create_multi_impl(index_dir, ndev, devices, out); });
 }
 
 extern "C" int ns_engine_create(const char* index_dir, int device, ns_engine** out) {
@@ -1069,10 +1087,14 @@ extern "C" int ns_engine_set_shard(ns_engine* e, int rank, int world) {
     return NS_OK;
 }
 
-extern "C" int ns_engine_reload(ns_engine* e) {
+static int ns_engine_reload_impl(ns_engine* e) {
     if (!e) { set_error("ns_engine_reload: null"); return NS_ERR_INVALID; }
     std::lock_guard<std::mutex> lk(e->reload_mu);
     return do_reload(e);
+}
+
+extern "C" int ns_engine_reload(ns_engine* e) {
+    return abi_guard("ns_engine_reload", NS_ERR_NOMEM, NS_ERR_STATE, [&]() -> int { return ns_engine_reload_impl(e); });
 }
 
 extern "C" int ns_engine_reload_stats(const ns_engine* e, double* total_s, double* read_upload_s, double* dict_s,
@@ -1101,7 +1123,7 @@ extern "C" int ns_engine_num_segments(const ns_engine* e) {
     return g ? (int)g->seg_names.size() : 0;
 }
 
-extern "C" int ns_engine_segment_name(const ns_engine* e, int i, char* buf, size_t cap) {
+static int ns_engine_segment_name_impl(const ns_engine* e, int i, char* buf, size_t cap) {
     if (!e || !buf) return -1;
     auto g = const_cast<ns_engine*>(e)->snapshot();
     if (!g || i < 0 || (size_t)i >= g->seg_names.size()) return -1;
@@ -1111,7 +1133,11 @@ extern "C" int ns_engine_segment_name(const ns_engine* e, int i, char* buf, size
     return (int)s.size();
 }
 
-extern "C" int ns_engine_segment_stats(const ns_engine* e, int i, uint32_t* N, float* avgdl, uint32_t* T, uint64_t* P) {
+extern "C" int ns_engine_segment_name(const ns_engine* e, int i, char* buf, size_t cap) {
+    return abi_guard("ns_engine_segment_name", -1, -1, [&]() -> int { return ns_engine_segment_name_impl(e, i, buf, cap); });
+}
+
+static int ns_engine_segment_stats_impl(const ns_engine* e, int i, uint32_t* N, float* avgdl, uint32_t* T, uint64_t* P) {
     if (!e) return NS_ERR_INVALID;
     auto g = const_cast<ns_engine*>(e)->snapshot();
     if (!g || i < 0 || (size_t)i >= g->segs.size() || !g->segs[(size_t)i]) { set_error("segment not loaded by this engine"); return NS_ERR_INVALID; }
@@ -1127,7 +1153,11 @@ extern "C" int ns_engine_segment_stats(const ns_engine* e, int i, uint32_t* N, f
     return NS_OK;
 }
 
-extern "C" int ns_engine_term_stats(const ns_engine* e, int i, const char* term, uint32_t* df, uint32_t* count) {
+extern "C" int ns_engine_segment_stats(const ns_engine* e, int i, uint32_t* N, float* avgdl, uint32_t* T, uint64_t* P) {
+    return abi_guard("ns_engine_segment_stats", NS_ERR_NOMEM, NS_ERR_STATE, [&]() -> int { return ns_engine_segment_stats_impl(e, i, N, avgdl, T, P); });
+}
+
+static int ns_engine_term_stats_impl(const ns_engine* e, int i, const char* term, uint32_t* df, uint32_t* count) {
     if (df) *df = 0;
     if (count) *count = 0;
     if (!e || !term) return NS_ERR_INVALID;
@@ -1140,12 +1170,16 @@ extern "C" int ns_engine_term_stats(const ns_engine* e, int i, const char* term,
     return NS_OK;
 }
 
+extern "C" int ns_engine_term_stats(const ns_engine* e, int i, const char* term, uint32_t* df, uint32_t* count) {
+    return abi_guard("ns_engine_term_stats", NS_ERR_NOMEM, NS_ERR_STATE, [&]() -> int { return ns_engine_term_stats_impl(e, i, term, df, count); });
+}
+
 extern "C" ns_index* ns_engine_index(ns_engine* e) { return e && !e->idx.empty() ? e->idx[0] : nullptr; }
 extern "C" ns_index* ns_engine_device_index(ns_engine* e, int slot) {
     return e && slot >= 0 && (size_t)slot < e->idx.size() ? e->idx[(size_t)slot] : nullptr;
 }
 
-extern "C" int ns_engine_cord_uid(const ns_engine* e, uint32_t seg, uint32_t doc, char* buf, size_t cap) {
+static int ns_engine_cord_uid_impl(const ns_engine* e, uint32_t seg, uint32_t doc, char* buf, size_t cap) {
     if (!e || !buf) return -1;
     auto g = const_cast<ns_engine*>(e)->snapshot();
     if (!g || seg >= g->segs.size() || !g->segs[seg]) return -1;
@@ -1153,6 +1187,10 @@ extern "C" int ns_engine_cord_uid(const ns_engine* e, uint32_t seg, uint32_t doc
     if (s.size() + 1 > cap) return -1;
     std::memcpy(buf, s.c_str(), s.size() + 1);
     return (int)s.size();
+}
+
+extern "C" int ns_engine_cord_uid(const ns_engine* e, uint32_t seg, uint32_t doc, char* buf, size_t cap) {
+    return abi_guard("ns_engine_cord_uid", -1, -1, [&]() -> int { return ns_engine_cord_uid_impl(e, seg, doc, buf, cap); });
 }
 
 namespace {
@@ -1182,13 +1220,18 @@ int resolve_abi(ns_engine* e, uint32_t Q, GetQuery get, uint64_t* q_off, ns_qter
 
 }  // namespace
 
-extern "C" int ns_engine_resolve_batch(ns_engine* e, uint32_t Q, const char* const* queries, uint64_t* q_off,
+static int ns_engine_resolve_batch_impl(ns_engine* e, uint32_t Q, const char* const* queries, uint64_t* q_off,
                                        ns_qterm* terms, uint64_t terms_cap, uint64_t* n_terms, uint8_t* has_terms) {
     if (!e || (Q && !queries) || !q_off || !n_terms) { set_error("ns_engine_resolve_batch: null argument"); return NS_ERR_INVALID; }
     return resolve_abi(e, Q, [&](uint32_t q) { return queries[q]; }, q_off, terms, terms_cap, n_terms, has_terms);
 }
 
-extern "C" int ns_engine_resolve_batch_packed(ns_engine* e, uint32_t Q, const char* zqueries, size_t nbytes,
+extern "C" int ns_engine_resolve_batch(ns_engine* e, uint32_t Q, const char* const* queries, uint64_t* q_off,
+                                       ns_qterm* terms, uint64_t terms_cap, uint64_t* n_terms, uint8_t* has_terms) {
+    return abi_guard("ns_engine_resolve_batch", NS_ERR_NOMEM, NS_ERR_STATE, [&]() -> int { return ns_engine_resolve_batch_impl(e, Q, queries, q_off, terms, terms_cap, n_terms, has_terms); });
+}
+
+static int ns_engine_resolve_batch_packed_impl(ns_engine* e, uint32_t Q, const char* zqueries, size_t nbytes,
                                               uint64_t* q_off, ns_qterm* terms, uint64_t terms_cap, uint64_t* n_terms,
                                               uint8_t* has_terms) {
     if (!e || (Q && !zqueries) || !q_off || !n_terms) { set_error("ns_engine_resolve_batch_packed: null argument"); return NS_ERR_INVALID; }
@@ -1200,7 +1243,13 @@ extern "C" int ns_engine_resolve_batch_packed(ns_engine* e, uint32_t Q, const ch
     return resolve_abi(e, Q, [&](uint32_t q) { return starts[q]; }, q_off, terms, terms_cap, n_terms, has_terms);
 }
 
-extern "C" int ns_engine_search_batch(ns_engine* e, uint32_t Q, const char* const* queries, int k, ns_hit* out_hits,
+extern "C" int ns_engine_resolve_batch_packed(ns_engine* e, uint32_t Q, const char* zqueries, size_t nbytes,
+                                              uint64_t* q_off, ns_qterm* terms, uint64_t terms_cap, uint64_t* n_terms,
+                                              uint8_t* has_terms) {
+    return abi_guard("ns_engine_resolve_batch_packed", NS_ERR_NOMEM, NS_ERR_STATE, [&]() -> int { return ns_engine_resolve_batch_packed_impl(e, Q, zqueries, nbytes, q_off, terms, terms_cap, n_terms, has_terms); });
+}
+
+static int ns_engine_search_batch_impl(ns_engine* e, uint32_t Q, const char* const* queries, int k, ns_hit* out_hits,
                                       uint32_t* out_nhits, uint64_t* out_found, uint8_t* has_found) {
     if (!e || (Q && !queries)) { set_error("ns_engine_search_batch: null argument"); return NS_ERR_INVALID; }
     auto gen = e->snapshot();
@@ -1211,7 +1260,12 @@ extern "C" int ns_engine_search_batch(ns_engine* e, uint32_t Q, const char* cons
                        out_hits, out_nhits, out_found, has_found);
 }
 
-extern "C" int ns_engine_search_batch_packed(ns_engine* e, uint32_t Q, const char* zqueries, size_t nbytes, int k,
+extern "C" int ns_engine_search_batch(ns_engine* e, uint32_t Q, const char* const* queries, int k, ns_hit* out_hits,
+                                      uint32_t* out_nhits, uint64_t* out_found, uint8_t* has_found) {
+    return abi_guard("ns_engine_search_batch", NS_ERR_NOMEM, NS_ERR_STATE, [&]() -> int { return ns_engine_search_batch_impl(e, Q, queries, k, out_hits, out_nhits, out_found, has_found); });
+}
+
+static int ns_engine_search_batch_packed_impl(ns_engine* e, uint32_t Q, const char* zqueries, size_t nbytes, int k,
                                              ns_hit* out_hits, uint32_t* out_nhits, uint64_t* out_found,
                                              uint8_t* has_found) {
     if (!e || (Q && !zqueries)) { set_error("ns_engine_search_batch_packed: null argument"); return NS_ERR_INVALID; }
@@ -1228,10 +1282,16 @@ extern "C" int ns_engine_search_batch_packed(ns_engine* e, uint32_t Q, const cha
                        out_hits, out_nhits, out_found, has_found);
 }
 
+extern "C" int ns_engine_search_batch_packed(ns_engine* e, uint32_t Q, const char* zqueries, size_t nbytes, int k,
+                                             ns_hit* out_hits, uint32_t* out_nhits, uint64_t* out_found,
+                                             uint8_t* has_found) {
+    return abi_guard("ns_engine_search_batch_packed", NS_ERR_NOMEM, NS_ERR_STATE, [&]() -> int { return ns_engine_search_batch_packed_impl(e, Q, zqueries, nbytes, k, out_hits, out_nhits, out_found, has_found); });
+}
+
 // Front end + prepare of a batch on a single-device engine, WITHOUT launching: tokenise, dictionary, kernel-form
 // records, pinned staging, H2D.  What a caller that drives the launch itself needs (nextsearch-api_b200/dist.py: one
 // process per GPU, launches ordered across ranks) — the same work ns_engine_search_batch_packed does before its launch.
-extern "C" int ns_engine_prepare_batch_packed(ns_engine* e, uint32_t Q, const char* zqueries, size_t nbytes, int k,
+static int ns_engine_prepare_batch_packed_impl(ns_engine* e, uint32_t Q, const char* zqueries, size_t nbytes, int k,
                                               ns_batch** out, uint8_t* has_found) {
     if (!e || !out || (Q && !zqueries)) { set_error("ns_engine_prepare_batch_packed: null argument"); return NS_ERR_INVALID; }
     *out = nullptr;
@@ -1246,6 +1306,7 @@ extern "C" int ns_engine_prepare_batch_packed(ns_engine* e, uint32_t Q, const ch
     const Generation& g = *gen;
     ResolveScratch sc;
     resolve_devices(e, g, Q, [&](uint32_t q, std::vector<QueryTerm>& qt) { return query_terms_of(g, starts[q], qt); }, sc);
+    if (sc.failed == 2) { set_error("front end: out of host memory"); return NS_ERR_NOMEM; }
     if (sc.failed) { set_error("semantic expansion: the device similarity scan failed"); return NS_ERR_CUDA; }
     if (has_found && Q) std::memcpy(has_found, sc.has.data(), Q);
     const DevResolved& r = sc.parts[0];
@@ -1261,10 +1322,15 @@ extern "C" int ns_engine_prepare_batch_packed(ns_engine* e, uint32_t Q, const ch
     return batch_prepare_on(e->idx[0], g.dev_state[0], Q, k, q_off.data(), qt.data(), out);
 }
 
+extern "C" int ns_engine_prepare_batch_packed(ns_engine* e, uint32_t Q, const char* zqueries, size_t nbytes, int k,
+                                              ns_batch** out, uint8_t* has_found) {
+    return abi_guard("ns_engine_prepare_batch_packed", NS_ERR_NOMEM, NS_ERR_STATE, [&]() -> int { return ns_engine_prepare_batch_packed_impl(e, Q, zqueries, nbytes, k, out, has_found); });
+}
+
 // Explicit qterms_w lists (the reference's vector<pair<string, float>> of src/api_engine.cpp:410-421), one per
 // query: t_off[Q+1] indexes terms[] / weights[].  No tokenisation, no filter, no expansion: exactly what the
 // scoring loop (:426-505) receives.
-extern "C" int ns_engine_search_terms_batch(ns_engine* e, uint32_t Q, const uint64_t* t_off, const char* const* terms,
+static int ns_engine_search_terms_batch_impl(ns_engine* e, uint32_t Q, const uint64_t* t_off, const char* const* terms,
                                             const float* weights, int k, ns_hit* out_hits, uint32_t* out_nhits,
                                             uint64_t* out_found, uint8_t* has_found) {
     if (!e || !t_off || (Q && t_off[Q] && (!terms || !weights))) { set_error("ns_engine_search_terms_batch: null argument"); return NS_ERR_INVALID; }
@@ -1284,10 +1350,16 @@ extern "C" int ns_engine_search_terms_batch(ns_engine* e, uint32_t Q, const uint
     return search_core(e, gen, Q, terms_of, k, out_hits, out_nhits, out_found, has_found);
 }
 
+extern "C" int ns_engine_search_terms_batch(ns_engine* e, uint32_t Q, const uint64_t* t_off, const char* const* terms,
+                                            const float* weights, int k, ns_hit* out_hits, uint32_t* out_nhits,
+                                            uint64_t* out_found, uint8_t* has_found) {
+    return abi_guard("ns_engine_search_terms_batch", NS_ERR_NOMEM, NS_ERR_STATE, [&]() -> int { return ns_engine_search_terms_batch_impl(e, Q, t_off, terms, weights, k, out_hits, out_nhits, out_found, has_found); });
+}
+
 // SemanticIndex::expand for one query (src/api_engine.cpp:410-417): the kept tokens are expanded with the
 // loaded embeddings.  Terms come back NUL-separated in `buf`, weights in `weights`; returns the count, -1
 // if a buffer is too small, 0 with *enabled = 0 when no embeddings are loaded.
-extern "C" int ns_engine_expand(ns_engine* e, const char* query, char* buf, size_t cap, float* weights, int wcap, int* enabled) {
+static int ns_engine_expand_impl(ns_engine* e, const char* query, char* buf, size_t cap, float* weights, int wcap, int* enabled) {
     if (enabled) *enabled = 0;
     if (!e || !query || !buf) return -1;
     auto gen = e->snapshot();
@@ -1309,20 +1381,33 @@ extern "C" int ns_engine_expand(ns_engine* e, const char* query, char* buf, size
     return n;
 }
 
-extern "C" int ns_engine_search_one(ns_engine* e, const char* query, int k, ns_hit* out_hits, uint32_t* out_nhits,
+extern "C" int ns_engine_expand(ns_engine* e, const char* query, char* buf, size_t cap, float* weights, int wcap, int* enabled) {
+    return abi_guard("ns_engine_expand", -1, -1, [&]() -> int { return ns_engine_expand_impl(e, query, buf, cap, weights, wcap, enabled); });
+}
+
+static int ns_engine_search_one_impl(ns_engine* e, const char* query, int k, ns_hit* out_hits, uint32_t* out_nhits,
                                     uint64_t* out_found, uint8_t* has_found) {
     if (!e || !query) { set_error("ns_engine_search_one: null argument"); return NS_ERR_INVALID; }
     if (e->idx.empty()) { set_error("engine was created without a CUDA device; there is no CPU search path"); return NS_ERR_STATE; }
     return search_one(e, query, k, out_hits, out_nhits, out_found, has_found, nullptr);
 }
 
-extern "C" int ns_engine_coalescer_start(ns_engine* e, uint32_t max_batch, uint32_t max_wait_us, int dispatchers) {
+extern "C" int ns_engine_search_one(ns_engine* e, const char* query, int k, ns_hit* out_hits, uint32_t* out_nhits,
+                                    uint64_t* out_found, uint8_t* has_found) {
+    return abi_guard("ns_engine_search_one", NS_ERR_NOMEM, NS_ERR_STATE, [&]() -> int { return ns_engine_search_one_impl(e, query, k, out_hits, out_nhits, out_found, has_found); });
+}
+
+static int ns_engine_coalescer_start_impl(ns_engine* e, uint32_t max_batch, uint32_t max_wait_us, int dispatchers) {
     if (!e) return NS_ERR_INVALID;
     if (e->idx.empty()) { set_error("engine was created without a CUDA device; there is no CPU search path"); return NS_ERR_STATE; }
     std::lock_guard<std::mutex> lk(e->co_mu);
     if (e->coalescer) { set_error("coalescer already running"); return NS_ERR_STATE; }
     e->coalescer.reset(new Coalescer(e, max_batch ? max_batch : 4096, max_wait_us, dispatchers > 0 ? dispatchers : 2));
     return NS_OK;
+}
+
+extern "C" int ns_engine_coalescer_start(ns_engine* e, uint32_t max_batch, uint32_t max_wait_us, int dispatchers) {
+    return abi_guard("ns_engine_coalescer_start", NS_ERR_NOMEM, NS_ERR_STATE, [&]() -> int { return ns_engine_coalescer_start_impl(e, max_batch, max_wait_us, dispatchers); });
 }
 
 extern "C" int ns_engine_coalescer_stop(ns_engine* e) {
@@ -1348,7 +1433,7 @@ extern "C" int ns_engine_coalescer_stats(ns_engine* e, uint64_t* batches, uint64
 // Load generator (bench tooling): `nthreads` host threads each issue `per_thread` blocking ns_engine_search_one
 // calls — the traffic shape of the reference's HTTP workers (src/api_server.cpp:117-178) without Python in the
 // loop.  Thread t starts at query (t * per_thread) % Q and walks the Q given queries cyclically.
-extern "C" int ns_engine_load_test(ns_engine* e, uint32_t nthreads, uint32_t per_thread, uint32_t Q, const char* zqueries,
+static int ns_engine_load_test_impl(ns_engine* e, uint32_t nthreads, uint32_t per_thread, uint32_t Q, const char* zqueries,
                                    size_t nbytes, int k, double* qps, double* p50_us, double* p99_us) {
     if (!e || !zqueries || Q == 0 || nthreads == 0 || per_thread == 0) { set_error("ns_engine_load_test: bad argument"); return NS_ERR_INVALID; }
     std::vector<const char*> starts;
@@ -1395,9 +1480,14 @@ extern "C" int ns_engine_load_test(ns_engine* e, uint32_t nthreads, uint32_t per
     return NS_OK;
 }
 
+extern "C" int ns_engine_load_test(ns_engine* e, uint32_t nthreads, uint32_t per_thread, uint32_t Q, const char* zqueries,
+                                   size_t nbytes, int k, double* qps, double* p50_us, double* p99_us) {
+    return abi_guard("ns_engine_load_test", NS_ERR_NOMEM, NS_ERR_STATE, [&]() -> int { return ns_engine_load_test_impl(e, nthreads, per_thread, Q, zqueries, nbytes, k, qps, p50_us, p99_us); });
+}
+
 // Engine::search (src/api_engine.cpp:369-542) as JSON text, byte-compatible with nlohmann's dump() of the
 // reference's object: keys in lexicographic order, floats via Grisu2 (json_text.hpp).
-extern "C" int ns_engine_search_json(ns_engine* e, const char* query, int k, char* buf, size_t cap, size_t* needed) {
+static int ns_engine_search_json_impl(ns_engine* e, const char* query, int k, char* buf, size_t cap, size_t* needed) {
     if (!e || !query) { set_error("ns_engine_search_json: null argument"); return NS_ERR_INVALID; }
     if (e->idx.empty()) { set_error("engine was created without a CUDA device; there is no CPU search path"); return NS_ERR_STATE; }
     const int K = std::max(1, std::min(k, NS_MAX_K));  // src/api_engine.cpp:377
@@ -1468,9 +1558,13 @@ extern "C" int ns_engine_search_json(ns_engine* e, const char* query, int k, cha
     return NS_OK;
 }
 
+extern "C" int ns_engine_search_json(ns_engine* e, const char* query, int k, char* buf, size_t cap, size_t* needed) {
+    return abi_guard("ns_engine_search_json", NS_ERR_NOMEM, NS_ERR_STATE, [&]() -> int { return ns_engine_search_json_impl(e, query, k, buf, cap, needed); });
+}
+
 // ------------------------------------------------------------------------------------------
 
-extern "C" int ns_text_query_terms(const char* query, char* buf, size_t cap) {
+static int ns_text_query_terms_impl(const char* query, char* buf, size_t cap) {
     if (!query || !buf) return -1;
     std::vector<std::string> terms;
     query_terms(query, terms);
@@ -1481,6 +1575,10 @@ extern "C" int ns_text_query_terms(const char* query, char* buf, size_t cap) {
         at += t.size() + 1;
     }
     return (int)terms.size();
+}
+
+extern "C" int ns_text_query_terms(const char* query, char* buf, size_t cap) {
+    return abi_guard("ns_text_query_terms", -1, -1, [&]() -> int { return ns_text_query_terms_impl(query, buf, cap); });
 }
 
 static CorpusSpec to_spec(const ns_corpus_spec* s) {
@@ -1494,7 +1592,7 @@ static CorpusSpec to_spec(const ns_corpus_spec* s) {
     return c;
 }
 
-extern "C" int ns_corpus_write_segment(const ns_corpus_spec* spec, uint64_t doc_base, uint32_t ndocs, const char* segdir,
+static int ns_corpus_write_segment_impl(const ns_corpus_spec* spec, uint64_t doc_base, uint32_t ndocs, const char* segdir,
                                        int write_forward, const char* dump_path, int nthreads) {
     if (!spec || !segdir) { set_error("ns_corpus_write_segment: null argument"); return NS_ERR_INVALID; }
     GenSegment g;
@@ -1504,7 +1602,12 @@ extern "C" int ns_corpus_write_segment(const ns_corpus_spec* spec, uint64_t doc_
     return NS_OK;
 }
 
-extern "C" int ns_corpus_write_manifest(const char* index_dir, uint32_t nseg, const char* const* names) {
+extern "C" int ns_corpus_write_segment(const ns_corpus_spec* spec, uint64_t doc_base, uint32_t ndocs, const char* segdir,
+                                       int write_forward, const char* dump_path, int nthreads) {
+    return abi_guard("ns_corpus_write_segment", NS_ERR_NOMEM, NS_ERR_STATE, [&]() -> int { return ns_corpus_write_segment_impl(spec, doc_base, ndocs, segdir, write_forward, dump_path, nthreads); });
+}
+
+static int ns_corpus_write_manifest_impl(const char* index_dir, uint32_t nseg, const char* const* names) {
     if (!index_dir || (nseg && !names)) return NS_ERR_INVALID;
     if (!make_dirs(index_dir)) { set_error("cannot create index dir"); return NS_ERR_IO; }
     std::vector<std::string> v;
@@ -1512,7 +1615,11 @@ extern "C" int ns_corpus_write_manifest(const char* index_dir, uint32_t nseg, co
     return save_manifest(std::string(index_dir) + "/manifest.bin", v) ? NS_OK : NS_ERR_IO;
 }
 
-extern "C" int ns_corpus_make_queries(const ns_corpus_spec* spec, uint64_t query_seed, uint32_t nq, uint32_t min_terms,
+extern "C" int ns_corpus_write_manifest(const char* index_dir, uint32_t nseg, const char* const* names) {
+    return abi_guard("ns_corpus_write_manifest", NS_ERR_NOMEM, NS_ERR_STATE, [&]() -> int { return ns_corpus_write_manifest_impl(index_dir, nseg, names); });
+}
+
+static int ns_corpus_make_queries_impl(const ns_corpus_spec* spec, uint64_t query_seed, uint32_t nq, uint32_t min_terms,
                                       uint32_t max_terms, uint32_t head_ranks, char* buf, size_t cap, size_t* needed) {
     if (!spec) return NS_ERR_INVALID;
     auto qs = make_queries(to_spec(spec), query_seed, nq, min_terms, max_terms, head_ranks);
@@ -1527,4 +1634,9 @@ extern "C" int ns_corpus_make_queries(const ns_corpus_spec* spec, uint64_t query
         at += q.size() + 1;
     }
     return NS_OK;
+}
+
+extern "C" int ns_corpus_make_queries(const ns_corpus_spec* spec, uint64_t query_seed, uint32_t nq, uint32_t min_terms,
+                                      uint32_t max_terms, uint32_t head_ranks, char* buf, size_t cap, size_t* needed) {
+    return abi_guard("ns_corpus_make_queries", NS_ERR_NOMEM, NS_ERR_STATE, [&]() -> int { return ns_corpus_make_queries_impl(spec, query_seed, nq, min_terms, max_terms, head_ranks, buf, cap, needed); });
 }

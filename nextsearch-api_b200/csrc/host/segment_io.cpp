@@ -82,6 +82,9 @@ bool parse_lexicon(const std::vector<uint8_t>& bytes, uint32_t barrel, uint64_t 
     Reader r(bytes.data(), bytes.size());
     uint32_t tcount = r.u32();
     if (!r.ok) { set_error("truncated lexicon header: " + what); return false; }
+    // an entry is at least 24 bytes (empty term): a count the file cannot hold is a corrupt header, not a reason to
+    // reserve gigabytes
+    if ((uint64_t)tcount * 24u > (uint64_t)(r.end - r.p)) { set_error("lexicon entry count exceeds the file size: " + what); return false; }
     rows.reserve(rows.size() + tcount);
     terms.reserve(terms.size() + tcount);
     for (uint32_t i = 0; i < tcount; i++) {
@@ -144,6 +147,8 @@ bool load_segment(const std::string& segdir, HostSegment& s, int nthreads, Posti
         Reader r(bytes.data(), bytes.size());
         uint32_t n = r.u32();
         if (!r.ok) { set_error("truncated docs.bin in " + segdir); return false; }
+        // a doc record is at least 16 bytes (three empty strings + doc_len)
+        if ((uint64_t)n * 16u > (uint64_t)(r.end - r.p)) { set_error("docs.bin document count exceeds the file size in " + segdir); return false; }
         s.doc_len.resize(n);
         s.uid_off.resize((size_t)n + 1);
         s.uid_chars.reserve((size_t)n * 12);
