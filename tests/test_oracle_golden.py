@@ -128,3 +128,28 @@ def test_product_writer_matches_live_reference_writer(workdir, vocab, seed, base
     ref = os.path.join(workdir, f"live_ref_{vocab}_{seed}")
     orc.ref_write_segment(dump, ref)
     assert sha_dir(mine) == sha_dir(ref)
+
+
+@pytest.mark.ref
+def test_oracle_matches_live_reference_on_messy_query_strings(small_case):
+    """Tokenisation and filtering (include/textutil.hpp:13-37, src/api_engine.cpp:388-397) through the whole search:
+    random mixtures of case, punctuation, digits, stopwords, one-letter tokens, tabs and valid multi-byte UTF-8."""
+    import random
+
+    rng = random.Random(77)
+    pieces = ["t1", "T2", "t3,", "(t4)", "t5-t6", "t7_t8", "the", "The", "a", "x", "of", "t9.", "t10!", "é", "t11é", "naïve", "t12\tt13",
+              "  ", "t14;t15", "zzzz", "9", "42", "t16/t17", "IS", "t18's", "\"t19\"", "ｔ２０", "t21 t22", "an", "t23?", "#t24", "t25+t26"]
+    queries = []
+    for _ in range(150):
+        q = " ".join(rng.choice(pieces) for _ in range(rng.randint(1, 7)))
+        queries.append(q)
+    queries = list(dict.fromkeys(queries))
+    oi = small_case.oracle
+    seg_index = {oi.segment_name(i): i for i in range(oi.num_segments)}
+    _, res = orc.ref_search(small_case.path, queries, 10)
+    assert len(res) == len(queries)
+    for q, r in zip(queries, res):
+        ref = {"query": q, "found": r.get("found"), "k": r["k"],
+               "hits": [(h["segment"], h["docId"], h["score_bits"]) for h in r["results"]]}
+        check_against_reference(oracle_result(oi, q, 10), ref, oi, seg_index)
+        assert nsb200.query_terms(q) == orc.query_terms(q), q          # the product's tokenizer gives the oracle's terms
