@@ -51,6 +51,17 @@ def corpora(workdir):
     a, b = os.path.join(workdir, "san_idx_a"), os.path.join(workdir, "san_idx_b")
     nsb200.build_index(a, nsb200.CorpusSpec(vocab=500), 600, 2)
     nsb200.build_index(b, nsb200.CorpusSpec(vocab=700, seed=5), 800, 3)
+    # result decoration and expansion data, so that the fuzz damages their parsers' inputs as well
+    import random
+    rng = random.Random(4)
+    with open(os.path.join(a, "metadata.csv"), "w", newline="") as f:
+        f.write("cord_uid,sha,source_x,title,doi,publish_time,authors,journal,url\n")
+        for d in range(0, 600, 3):
+            f.write(f'uid{d},s{d},PMC,"Title, {d} ""quoted""",10.1/{d},2020-0{1 + d % 9}-11,"Last{d}, First; Other, A",J,https://x.example/{d}; https://y.example/{d}\n')
+    with open(os.path.join(a, "embeddings.vec"), "w", newline="") as f:
+        f.write("200 16\n")
+        for r in range(1, 201):
+            f.write(f"t{r} " + " ".join(f"{rng.gauss(0, 1):.4f}" for _ in range(16)) + "\n")
     return a, b
 
 

@@ -45,10 +45,14 @@ static int fuzzload(const char* index_dir, const char* scratch, int iters, unsig
         fs::path work = fs::path(scratch) / ("fz" + std::to_string(it % 4));
         fs::remove_all(work);
         fs::copy(index_dir, work, fs::copy_options::recursive);
-        // prefer the small structured files; inverted barrels are validated on the device, not here
+        // prefer the small structured files; inverted barrels are validated on the device, not here.  Three times in ten
+        // the victim is a top-level file: manifest.bin, metadata.csv, the embeddings file.
+        std::vector<fs::path> top;
+        for (auto& f : files)
+            if (!f.has_parent_path()) top.push_back(f);
         fs::path victim;
         for (int tries = 0; tries < 64; tries++) {
-            victim = files[rng() % files.size()];
+            victim = (!top.empty() && rng() % 10 < 3) ? top[rng() % top.size()] : files[rng() % files.size()];
             const std::string n = victim.filename().string();
             if (n.rfind("inverted", 0) != 0 && n.rfind("forward", 0) != 0 && n.rfind("terms", 0) != 0) break;
         }
